@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- clip-frames/s of the CFFM hot path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): MiT-B1 + CFFM head (depth 2), 480x480, T=4, batch 2 clips per GPU,
+synthetic N(0,1) frames, synthetic weights (vss_cffm_b200.synth), 124 classes.  One "step" = one
+EncoderDecoder_clips inference pass over one batch: frames -> int64 label maps.
+
+  value : clip-frames/s (B*T*N / max-over-ranks device time), inputs resident in HBM, labels left in HBM
+  e2e   : same metric through the public API with HOST (pinned) frames: H2D copy, forward, D2H of labels
+          inside the timed region
+  roofline     : the CFM attention kernel (the kernel the metric names), timed live with CUDA events
+  cpu_baseline : the CPU oracle (a port of the reference's PyTorch path) on this box's host cores, bounded sample
+
+N>1: clips shard across ranks (the reference's own data-parallel strategy): weak
+scaling, no data-path collective; `--shard frames` exercises the frame-sharded path with one NCCL
+all-gather of the reference-frame features.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "clip-frames/sec (480x480, T=4, MiT-B1+CFFM)"
+UNIT = "clip-frames/s"
+H = W = 480
+T = 4
+CLIPS_PER_GPU = 2
+VARIANT = "b1"
+CFM_FLOPS_PER_CLIP_BLOCK = 2 * 2 * 81 * 8 * 49 * 289 * 32            # QK^T + PV, SURVEY.md 8(d): 1.1746 GFLOP
+# fp16 operands each once, per clip per block: Q + target K,V + pooled K,V + O + bias tables
+CFM_BYTES_PER_CLIP_BLOCK = (3969 * 256 * 2) + (3969 * 512 * 2) + (1215 * 512 * 2) + (3600 * 256 * 2) + (8 * 49 * 289 * 4)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shard", default="clips", choices=["clips", "frames"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        self.f.close()
+        os.unlink(self.f.name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def oracle_state(seed=21):
+    """Weights for the CPU oracle: the same synthetic state dict the GPU model is filled with."""
+    import vss_cffm_b200 as V
+    from vss_cffm_b200 import synth
+    m = V.build_segmentor(V.model_cfg(VARIANT))
+    synth.fill_module(m, seed)
+    return m, {k: v.clone() for k, v in m.state_dict().items()}
+
+
+def cpu_reference_time(sd, steps, warmup, clips=1):
+    """Times the CPU oracle (oracle/cffm_oracle.py: plain fp32 PyTorch restatement of the reference's
+    EncoderDecoder_clips forward) on `clips` clips per step with every host thread torch will use."""
+    import torch
+    from oracle import cffm_oracle as O
+    from vss_cffm_b200 import synth
+    torch.set_grad_enabled(False)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    imgs = synth.synth_clip(clips, T, H, W, seed=3)
+    for _ in range(warmup):
+        O.segmentor_simple_test(sd, imgs, "mit_" + VARIANT, 2)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.segmentor_simple_test(sd, imgs, "mit_" + VARIANT, 2).numpy()
+        ts.append(time.perf_counter() - t0)
+    mean = sum(ts) / len(ts)
+    return clips * T / mean, mean * 1e3, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    _, sd = oracle_state()
+    steps = max(1, min(args.steps, 8))                       # bounded: ~2 s per clip on 8 cores
+    value, ms, cores = cpu_reference_time(sd, steps, max(1, min(args.warmup, 1)), clips=1)
+    sample = f"1 clip (T={T}, {H}x{W}) per step, {steps} timed steps after 1 warm-up, fp32, {cores} torch threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"MiT-B1 + CFFM (depth 2), {H}x{W}, T={T}, reference's PyTorch path on host CPU cores",
+                   "note": "the reference is pure Python/PyTorch+mmcv (mmcv absent offline); this is oracle/cffm_oracle.py, the "
+                           "CPU port pinned to goldens generated from the unmodified reference"},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    import vss_cffm_b200 as V
+    from vss_cffm_b200 import _abi, ops, synth
+    torch.set_grad_enabled(False)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA (sm_100) device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    _abi.require_device()
+    assert _abi.load().cffm_current_device() == local_rank
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.gpus != world and rank == 0 and world > 1:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    n_gpus = world
+
+    model, sd = oracle_state()
+    model = model.cuda().eval()
+    B = CLIPS_PER_GPU
+    imgs_host = [t.pin_memory() for t in synth.synth_clip(B, T, H, W, seed=100 + rank)]
+    imgs_dev = [t.cuda() for t in imgs_host]
+    metas = synth.img_metas(B, H, W)
+    labels_host = torch.empty(B, H, W, dtype=torch.int64).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    if args.shard == "frames" and world > 1:
+        from vss_cffm_b200 import parallel
+        runner = parallel.FrameShardedRunner(model, world, rank)
+        step_dev = lambda: runner.predict_labels(imgs_dev, metas)
+    else:
+        step_dev = lambda: model.predict_labels(imgs_dev, metas)
+
+    def step_e2e():
+        lab = model.predict_labels(imgs_host, metas)          # H2D of the pinned frames happens inside
+        labels_host.copy_(lab, non_blocking=True)
+        return lab
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """Sum of per-step CUDA-event times; L2 is flushed between steps outside the events."""
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    n0 = _abi.n_launches
+    with ops.KernelTimer({"cffm_cfm_attention"}) as kt:
+        total_ms = timed(step_dev, args.steps)
+    launches = _abi.n_launches - n0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    cfm_ms = kt.ms()["cffm_cfm_attention"]
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    e2e_ms = timed(step_e2e, args.steps)
+    barrier()
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = t.tolist()
+    frames = B * T * n_gpus * args.steps
+    value = frames / (total_ms * 1e-3)
+    e2e_value = frames / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        pk = peaks()
+        cfm_avg_ms = sum(cfm_ms) / max(len(cfm_ms), 1)
+        alg_bytes = CFM_BYTES_PER_CLIP_BLOCK * B                              # one launch = B clips of one block
+        alg_flops = CFM_FLOPS_PER_CLIP_BLOCK * B
+        gbs = alg_bytes / (cfm_avg_ms * 1e-3) / 1e9
+        tfs = alg_flops / (cfm_avg_ms * 1e-3) / 1e12
+        roofline = {"kernel": "cfm_attention_kernel", "bound": "hbm", "achieved": round(gbs, 2), "peak": pk["hbm"],
+                    "unit": "GB/s", "frac": round(gbs / pk["hbm"], 5), "traffic": None,
+                    "tensor_tflops": round(tfs, 3), "tensor_frac_of_sustained": round(tfs / pk["tf_sust"], 5),
+                    "launch_ms": round(cfm_avg_ms, 5), "launches_timed": len(cfm_ms), "peak_source": pk["src"],
+                    "share_of_step": round(sum(cfm_ms) / total_ms, 4),
+                    "algorithmic": {"bytes_per_launch": alg_bytes, "flops_per_launch": alg_flops,
+                                    "note": "SURVEY.md 8(d): 9.6 MB and 1.1746 GFLOP per clip per block; un-fused attention "
+                                            "has AI 122 FLOP/B < ridge 210, so HBM is the binding roof"}}
+        out = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+            "config": {"workload": f"MiT-B1 + CFFM head (depth 2), {H}x{W}, T={T}, {B} clips per GPU (BASELINE configs[1])",
+                       "clips_per_gpu": B, "frames_per_step": B * T * n_gpus, "shard": args.shard if n_gpus > 1 else "none",
+                       "l2": "256 MiB flush between timed steps", "timing": "per-step CUDA events, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms / args.steps, 4),
+                    "h2d_bytes_per_step": B * T * 3 * H * W * 4, "d2h_bytes_per_step": B * H * W * 8,
+                    "api": "EncoderDecoder_clips.predict_labels(pinned host frames) + D2H of the int64 label maps"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+        }
+        if not args.no_cpu_baseline:
+            v, ms, cores = cpu_reference_time(sd, 3, 1, clips=1)
+            out["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"1 clip (T={T}, {H}x{W}), 3 timed forwards after 1 warm-up, fp32 CPU oracle, "
+                                             f"{ms:.0f} ms per clip"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

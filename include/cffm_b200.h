@@ -1,0 +1,163 @@
+/*
+ * cffm_b200.h -- C ABI of the B200-native CFFM hot path (libcffm_b200.so).
+ *
+ * Drop-in boundary.  The reference (GuoleiSun/VSS-CFFM) is pure Python on PyTorch + mmcv
+ * (setup.py:125 ext_modules=[]): it has no FFI of its own.  Its hot path is the chain of
+ * nn.Module.forward methods below; a maintainer binds this library with ctypes (see
+ * INTEGRATION.md) from inside those forward methods.  Each entry point names the reference
+ * code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - plain pointers and sizes; no torch types.  Every pointer is a DEVICE pointer on the
+ *    current CUDA device unless it is documented as host memory.
+ *  - activations are token-major ("NHWC"): row = (frame, y, x), channels contiguous.
+ *    `half` = IEEE fp16 (GEMM / attention operands), `float` = fp32 (residual streams,
+ *    LayerNorm / softmax statistics, accumulators).  ld* = row stride in ELEMENTS.
+ *  - weights are fp16 [N_out, K] row-major (torch.nn.Linear layout).
+ *  - `stream` is a cudaStream_t passed as void*.  All calls are asynchronous on it, never
+ *    allocate, never synchronise, keep no global state (re-entrant per stream; capturable
+ *    in a CUDA graph).  The caller owns all memory (PyTorch stays the allocator).
+ *  - return value: 0 = ok, >0 = CFFM_E_* (bad argument / unsupported shape / arch),
+ *    <0 = -(cudaError_t).  Nothing throws across the ABI.  cffm_last_error() gives a
+ *    thread-local human-readable message for the last non-zero status.
+ *  - there is NO CPU fallback: without an sm_100 device every compute entry point fails.
+ */
+#ifndef CFFM_B200_H_
+#define CFFM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFFM_ABI_VERSION 1
+
+enum {
+  CFFM_OK = 0,
+  CFFM_E_BADARG = 1,      /* null pointer, negative size, misaligned pointer or stride   */
+  CFFM_E_UNSUPPORTED = 2, /* shape outside what the kernels are built for                */
+  CFFM_E_ARCH = 3,        /* current device is not compute capability 10.x               */
+  CFFM_E_DRIVER = 4       /* cuTensorMapEncodeTiled unavailable / failed                 */
+};
+
+enum { CFFM_ACT_NONE = 0, CFFM_ACT_GELU = 1, CFFM_ACT_RELU = 2 };
+enum { CFFM_GEMM_TCGEN05 = 0, CFFM_GEMM_CHECK = 1 };
+
+int cffm_abi_version(void);
+const char* cffm_last_error(void);
+/* 0 when the current device can run this library (sm_100 family). */
+int cffm_device_check(void);
+/* Ordinal of the device the library will launch on (the caller's current CUDA context), or
+ * -(cudaError_t).  Lets a multi-process host assert that rank r really drives GPU r. */
+int cffm_current_device(void);
+
+/* out = act(A[M,K] . W[N,K]^T + bias[N]) (+ residual[M,N]); fp16 operands, fp32 accumulate.
+ * Replaces every nn.Linear / 1x1 nn.Conv2d / (with cffm_im2col) k x k nn.Conv2d on the path:
+ * mix_transformer.py:49,53,98,104,114,173-195  cffm_head.py:36,119,123,148
+ * cffm_transformer.py:21-24,374,449,495,602  swin_transformer_2d.py:219,223,258.
+ * bias, residual, out_f16, out_f32 may each be NULL (at least one output is required).
+ * residual is fp32 [M, ldr] and may alias out_f32 (in-place residual stream).
+ * Requires K % 8 == 0, N % 8 == 0, lda/ldw % 8 == 0, 16-byte aligned A/W/outputs.
+ * impl: CFFM_GEMM_TCGEN05 = TMA + tcgen05.mma + TMEM kernel (the product path);
+ *       CFFM_GEMM_CHECK   = simple CUDA-core kernel used by the tests to cross-check. */
+int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                  const float* residual, int64_t ldr, void* out_f16, int64_t ldo16,
+                  float* out_f32, int64_t ldo32, int M, int N, int K, int act, int impl,
+                  void* stream);
+
+/* Row LayerNorm over C channels, fp32 statistics.  x is fp32 (x_is_f32=1) or fp16.
+ * Writes fp16 and/or fp32.  mix_transformer.py:154-155,198,321  cffm_transformer.py:824
+ * swin_transformer_2d.py:619,622,663. */
+int cffm_layernorm(const void* x, int x_is_f32, int64_t ldx, const float* gamma, const float* beta,
+                   float eps, void* out_f16, int64_t ldo16, float* out_f32, int64_t ldo32,
+                   int M, int C, void* stream);
+
+/* Patch extraction for conv-as-GEMM: A[(n,oy,ox), (ky,kx,c)] fp16 with row stride Kpad
+ * (columns >= k*k*C are zero-filled).  layout 0: x = fp32 NCHW image (N,C,H,W);
+ * layout 1: x = fp16 NHWC (N,H,W,C).  Zero padding `pad`.
+ * OverlapPatchEmbed.proj (mix_transformer.py:173-195) and the k=s spatial-reduction conv
+ * Attention.sr (mix_transformer.py:76,101-102). */
+int cffm_im2col(const void* x, int layout, int N, int H, int W, int C, int k, int stride, int pad,
+                void* A, int Kpad, void* stream);
+
+/* softmax(scale * q k^T) v for small key sets held in shared memory.
+ * q [batch, Nq, heads*head_dim] (row stride ldq), k/v [batch, Nkv, ...] (row stride ldkv),
+ * out [batch, Nq, heads*head_dim] (row stride ldo); head h uses columns [h*head_dim, ...).
+ * head_dim in {32, 64}.  MiT efficient attention (mix_transformer.py:109-113) and the CFFM++
+ * prototype cross-attention (swin_transformer_2d.py:226-257). */
+int cffm_mha_f16(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
+                 int64_t ldo, int batch, int Nq, int Nkv, int heads, int head_dim, float scale,
+                 void* stream);
+
+/* Mix-FFN middle: depthwise 3x3 conv (pad 1) + bias + exact GELU on fp16 NHWC.
+ * w is fp16 [9, C] (tap-major), bias fp32 [C].  mix_transformer.py:50-51,361-368. */
+int cffm_dwconv3x3_gelu(const void* x, const void* w, const float* bias, void* out, int N, int H,
+                        int W, int C, void* stream);
+
+/* SegFormer MLP-decoder fuse after weight folding (linear_c{i} . linear_fuse . BN folded on the
+ * host): c = relu(p1 + up(p2) + up(p3) + up(p4) + shift), bilinear align_corners=False
+ * upsampling of the coarser maps to (H1,W1).  p_i fp16 NHWC [N,Hi,Wi,C].
+ * c_full (fp16 [N,H1,W1,C], may be NULL) receives _c; c_half_f32 / c_half_f16 (may be NULL)
+ * receive the 2x2 mean = resize(_c, 1/2) (cffm_head.py:108-119,131-133).
+ * T_perm > 1: the N input frames are in the reference's clip-major order (n = b*T + t,
+ * encoder_decoder.py:557) and every output is written frame-major (slot t*B + b), the layout
+ * the CFFA/CFM entry points use (target frames contiguous at the end); T_perm <= 1: no reorder. */
+int cffm_head_fuse(const void* p1, const void* p2, const void* p3, const void* p4, int N, int H1,
+                   int W1, int H2, int W2, int H3, int W3, int H4, int W4, int C, int T_perm,
+                   const float* shift, void* c_full, float* c_half_f32, int64_t ldh32,
+                   void* c_half_f16, int64_t ldh16, void* stream);
+
+/* CFFA step 1: LayerNorm (norm1) of all T frames of x fp32 [T,B,H,W,C] (frame-major; the target
+ * frames are the last B) -> xn fp16 (same shape)
+ * and the zero-padded target map xt_pad fp16 [B,Hp,Wp,C] (interior rows only are written; the
+ * caller zeroes the pad rows once).  cffm_transformer.py:713-734. */
+int cffm_cffa_norm(const float* x, const float* gamma, const float* beta, float eps, void* xn,
+                   void* xt_pad, int B, int T, int H, int W, int Hp, int Wp, int C, void* stream);
+
+/* CFFA step 2: coarse-to-fine pooling of the (virtually zero-padded) LN'ed frames.
+ * xn fp16 [T,B,H,W,C] frame-major.  pooled fp16 [B, P, C], P = nW*(1+1+4+9): target 7x7 fc-pool | ref0 7x7 | ref1 bilinear
+ * (Hp->6*nWh) + 3x3 | ref2 bilinear + 2x2, each map row-major.  pool_w fp32 packed
+ * [49+49+9+4], pool_b fp32 [4].  cffm_transformer.py:739-805. */
+int cffm_cffa_pool(const void* xn, int B, int T, int H, int W, int C, const float* pool_w,
+                   const float* pool_b, void* pooled, void* stream);
+
+/* Cross-frame feature mining attention with in-kernel K/V assembling (no roll / partition /
+ * unfold / cat is materialised).  qkv_t fp16 [B, Hp*Wp, 3C] = qkv(xt_pad); kv_pooled fp16
+ * [B, P, 2C] = K,V thirds of qkv(pooled); bias fp32 [heads, 64, 320] = window-independent
+ * additive term (relative-position tables gathered on the host, rows >= 49 / cols >= 289
+ * ignored).  out fp16 [B, H*W, C]: window_reverse + crop already applied.
+ * C = 256, heads = 8, window 7, expand 3 (the head's hard-coded setting, cffm_head.py:74-95).
+ * cffm_transformer.py:364-601 and :809-821. */
+int cffm_cfm_attention(const void* qkv_t, const void* kv_pooled, const float* bias, void* out, int B,
+                       int H, int W, int C, int heads, float scale, void* stream);
+
+/* Debug/test entry: the (level, y, x) source of every key slot exactly as the attention kernel
+ * computes it; out int32 [nW, 289, 3], y = x = -1 for zero-filled slots. */
+int cffm_cfm_key_sources(int Hp, int Wp, int32_t* out, void* stream);
+
+/* Bilinear (align_corners=False) resize of NHWC logits to fp32 NCHW.
+ * in: fp16 (in_is_f32=0) or fp32 [B,h,w,ldc] using the first ncls channels.
+ * cffm_head.py:149 (x2 -> 1/4 scale), mmseg/ops/wrappers.py:8-29. */
+int cffm_resize_nhwc_to_nchw(const void* in, int in_is_f32, int64_t ldc, float* out, int B, int h,
+                             int w, int ncls, int Ho, int Wo, void* stream);
+
+/* Fused bilinear resize (align_corners=False) of fp32 NCHW logits to (Ho,Wo) + argmax over
+ * channels -> int64 labels [B,Ho,Wo].  softmax is monotone, so it is skipped.
+ * encoder_decoder.py:373-377,542,564. */
+int cffm_resize_argmax(const float* logits, int64_t* labels, int B, int ncls, int h, int w, int Ho,
+                       int Wo, void* stream);
+
+/* Bilinear (align_corners=False) resize of fp32 NCHW maps [B,C,h,w] -> [B,C,Ho,Wo]: the extra
+ * "rescale to ori_shape" step of whole_inference (encoder_decoder.py:507-514). */
+int cffm_resize_nchw(const float* in, float* out, int B, int C, int h, int w, int Ho, int Wo,
+                     void* stream);
+
+/* softmax over the class dimension of fp32 NCHW logits (encoder_decoder.py:542); only needed when
+ * a caller asks for probabilities -- simple_test's argmax skips it. */
+int cffm_softmax_nchw(const float* in, float* out, int B, int C, int64_t HW, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFFM_B200_H_ */

@@ -1,0 +1,349 @@
+"""Per-kernel parity: every C-ABI entry point vs the CPU oracle / a plain fp32 PyTorch restatement of
+the same op on the same seeded inputs (inputs are rounded to fp16 first, so the comparison isolates
+the kernel: fp32 accumulation order + one fp16 output rounding).
+
+Tolerance (north_star: 1e-3 relative in fp16): max|gpu - ref| <= 1e-3 * max|ref| for fp16 outputs,
+1e-4 for fp32 outputs; integer / index work is bit-exact."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cffm_oracle as O
+from vss_cffm_b200 import cffm_tables as tb
+from vss_cffm_b200 import synth
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+REL16, REL32 = 1e-3, 1e-4
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vss_cffm_b200 import _abi, ops as _ops
+    _abi.require_device()
+    return _ops
+
+
+def h16(t):
+    """fp32 tensor rounded to fp16-representable values."""
+    return t.half().float()
+
+
+def rel_err(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def check(a, b, tol, what=""):
+    e = rel_err(a, b)
+    assert e <= tol, f"{what}: rel err {e:.3e} > {tol:.1e}"
+    return e
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+GEMM_SHAPES = [
+    # (M, N, K)  -- tails in M, N < tile, K < 64, K not a multiple of 64, the real path shapes
+    (128, 64, 64), (300, 32, 32), (1000, 256, 152), (4100, 768, 256), (257, 128, 576), (513, 320, 1152),
+    (225, 512, 2880), (450, 64, 4096), (3600, 1024, 256), (3600, 256, 1024), (129, 128, 512), (64, 8, 8),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_tcgen05_vs_fp32(ops, M, N, K):
+    a = h16(synth.synth_array((M, K), 1)).cuda()
+    w = h16(synth.synth_array((N, K), 2, scale=K ** -0.5)).cuda()
+    bias = synth.synth_array((N,), 3).cuda()
+    res = synth.synth_array((M, N), 4).cuda()
+    ref = a.double() @ w.double().t() + bias.double()
+    # plain: bias only, both outputs
+    o16 = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    o32 = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm(a.half(), w.half(), bias=bias, out16=o16, out32=o32)
+    check(o32, ref, REL32, "gemm f32")
+    check(o16, ref, REL16, "gemm f16")
+    # cross-check kernel agrees too
+    c32 = torch.empty_like(o32)
+    ops.gemm(a.half(), w.half(), bias=bias, out32=c32, impl=ops.GEMM_CHECK)
+    check(c32, ref, REL32, "gemm check impl")
+    # GELU + residual, in place on the residual buffer
+    ref2 = F.gelu(ref) + res.double()
+    inplace = res.clone()
+    ops.gemm(a.half(), w.half(), bias=bias, residual=inplace, out32=inplace, act=ops.ACT_GELU)
+    check(inplace, ref2, REL32, "gemm gelu+residual in place")
+    # ReLU, no bias
+    ops.gemm(a.half(), w.half(), out32=o32, act=ops.ACT_RELU)
+    check(o32, F.relu(a.double() @ w.double().t()), REL32, "gemm relu")
+
+
+def test_gemm_strided_operands(ops):
+    """Column-sliced W (ldw > K), row-sliced W and a strided output: the classifier / qkv call sites."""
+    M, K = 500, 256
+    a = h16(synth.synth_array((M, K), 5)).cuda().half()
+    wfull = h16(synth.synth_array((128, 2 * K), 6, scale=0.05)).cuda().half()
+    out = torch.zeros(M, 128, dtype=torch.float32, device="cuda")
+    ops.gemm(a, wfull[:, :K], out32=out)
+    ops.gemm(a, wfull[:, K:], residual=out, out32=out)
+    ref = a.double() @ wfull[:, :K].double().t() + a.double() @ wfull[:, K:].double().t()
+    check(out, ref, REL32, "two-part classifier")
+    w3 = h16(synth.synth_array((768, K), 7, scale=0.05)).cuda().half()
+    big = torch.zeros(M, 1024, dtype=torch.float16, device="cuda")
+    ops.gemm(a, w3[256:], out16=big[:, 512:])
+    check(big[:, 512:], a.double() @ w3[256:].double().t(), REL16, "row-sliced W, strided out")
+    assert big[:, :512].abs().max().item() == 0
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    from vss_cffm_b200._abi import CffmError
+    a = torch.zeros(16, 12, dtype=torch.float16, device="cuda")
+    w = torch.zeros(8, 12, dtype=torch.float16, device="cuda")
+    o = torch.zeros(16, 8, dtype=torch.float32, device="cuda")
+    with pytest.raises(CffmError, match="UNSUPPORTED"):
+        ops.gemm(a, w, out32=o)                                  # K % 8 != 0
+    with pytest.raises(CffmError):
+        ops.gemm(a.cpu(), w, out32=o)                            # no CPU fallback
+
+
+# ------------------------------------------------------------------------------------ elementwise
+@pytest.mark.parametrize("M,C,f32in", [(1000, 64, True), (77, 320, True), (513, 512, False), (9, 32, True), (300, 256, False)])
+def test_layernorm(ops, M, C, f32in):
+    x = synth.synth_array((M, C), 8, scale=2.0)
+    if not f32in:
+        x = h16(x)
+    g, b = synth.synth_array((C,), 9) * 0.1 + 1, synth.synth_array((C,), 10) * 0.1
+    for eps in (1e-5, 1e-6):
+        ref = F.layer_norm(x.double(), (C,), g.double(), b.double(), eps)
+        o16 = torch.empty(M, C, dtype=torch.float16, device="cuda")
+        o32 = torch.empty(M, C, dtype=torch.float32, device="cuda")
+        ops.layernorm(x.cuda() if f32in else x.cuda().half(), g.cuda(), b.cuda(), eps, out16=o16, out32=o32)
+        check(o32, ref, REL32, "layernorm f32")
+        check(o16, ref, REL16, "layernorm f16")
+
+
+@pytest.mark.parametrize("layout,N,H,W,C,k,s,p", [(0, 2, 64, 96, 3, 7, 4, 3), (1, 2, 16, 24, 64, 3, 2, 1),
+                                                  (1, 1, 16, 24, 32, 8, 8, 0), (1, 3, 9, 7, 160, 3, 2, 1),
+                                                  (1, 2, 8, 12, 128, 4, 4, 0)])
+def test_im2col_bit_exact(ops, layout, N, H, W, C, k, s, p):
+    x = h16(synth.synth_array((N, C, H, W), 11))
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    kdim = k * k * C
+    kpad = (kdim + 7) // 8 * 8
+    out = torch.full((N * Ho * Wo, kpad), 7.0, dtype=torch.float16, device="cuda")
+    src = x.cuda().contiguous() if layout == 0 else x.permute(0, 2, 3, 1).contiguous().cuda().half()
+    ops.im2col(src, layout, N, H, W, C, k, s, p, out)
+    cols = F.unfold(x, k, padding=p, stride=s)                               # (N, C*k*k, L), order (c, ky, kx)
+    ref = cols.view(N, C, k, k, Ho * Wo).permute(0, 4, 2, 3, 1).reshape(N * Ho * Wo, kdim)
+    assert torch.equal(out[:, :kdim].float().cpu(), ref)
+    assert out[:, kdim:].abs().max().item() == 0 if kpad > kdim else True
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 24, 256), (1, 7, 5, 128), (3, 4, 6, 1280)])
+def test_dwconv3x3_gelu(ops, N, H, W, C):
+    x = h16(synth.synth_array((N, C, H, W), 12))
+    w = h16(synth.synth_array((C, 1, 3, 3), 13, scale=0.3))
+    b = synth.synth_array((C,), 14, scale=0.1)
+    ref = F.gelu(F.conv2d(x.double(), w.double(), b.double(), padding=1, groups=C)).permute(0, 2, 3, 1)
+    out = torch.empty(N, H, W, C, dtype=torch.float16, device="cuda")
+    ops.dwconv3x3_gelu(x.permute(0, 2, 3, 1).contiguous().cuda().half(), w.view(C, 9).t().contiguous().cuda().half(),
+                       b.cuda(), out, N, H, W, C)
+    check(out, ref, REL16, "dwconv+gelu")
+
+
+@pytest.mark.parametrize("B,Nq,Nkv,heads,d", [(2, 384, 6, 1, 64), (2, 96, 6, 2, 64), (3, 200, 225, 5, 64),
+                                              (2, 225, 225, 8, 64), (2, 100, 10, 8, 32), (1, 3600, 64, 8, 32),
+                                              (2, 130, 100, 1, 32)])
+def test_mha_small_kv(ops, B, Nq, Nkv, heads, d):
+    C = heads * d
+    q = h16(synth.synth_array((B, Nq, C), 15))
+    kv = h16(synth.synth_array((B, Nkv, 2 * C), 16))
+    scale = d ** -0.5
+    qh = q.double().view(B, Nq, heads, d).transpose(1, 2)
+    kh = kv[..., :C].double().view(B, Nkv, heads, d).transpose(1, 2)
+    vh = kv[..., C:].double().view(B, Nkv, heads, d).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1) @ vh).transpose(1, 2).reshape(B * Nq, C)
+    out = torch.empty(B * Nq, C, dtype=torch.float16, device="cuda")
+    kvd = kv.view(B * Nkv, 2 * C).cuda().half()
+    ops.mha(q.view(B * Nq, C).cuda().half(), kvd[:, :C], kvd[:, C:], out, B, Nq, Nkv, heads, d, scale)
+    check(out, ref, 2e-3, "mha")       # P is rounded to fp16 before P.V: 2 fp16 roundings on the path
+
+
+# ----------------------------------------------------------------------------------- head decoder
+def _head_sd(seed, chans):
+    spec = {f"linear_c{i + 1}.proj.weight": (256, c) for i, c in enumerate(chans)}
+    spec.update({f"linear_c{i + 1}.proj.bias": (256,) for i in range(4)})
+    spec.update({"linear_fuse.conv.weight": (256, 1024, 1, 1), "linear_fuse.bn.weight": (256,),
+                 "linear_fuse.bn.bias": (256,), "linear_fuse.bn.running_mean": (256,), "linear_fuse.bn.running_var": (256,)})
+    return synth.synth_state_dict(spec, seed)
+
+
+@pytest.mark.parametrize("t_perm", [0, 4])
+def test_head_fuse_vs_oracle(ops, t_perm):
+    """Folded MLP decoder + 2x2 mean == oracle head_mlp_decoder + resize(1/2) (cffm_head.py:102-133)."""
+    chans, N, h, w = [64, 128, 320, 512], 4, 16, 24
+    sd = _head_sd(17, chans)
+    feats = [h16(synth.synth_array((N, c, h >> i, w >> i), 18 + i)) for i, c in enumerate(chans)]
+    c_ref = O.head_mlp_decoder(sd, "", feats)                                      # (N,256,h,w)
+    half_ref = O.resize(c_ref, (h // 2, w // 2))
+    # host-side fold (same algebra as CFFMHead._build_plan)
+    s = sd["linear_fuse.bn.weight"].double() / torch.sqrt(sd["linear_fuse.bn.running_var"].double() + 1e-5)
+    shift = sd["linear_fuse.bn.bias"].double() - sd["linear_fuse.bn.running_mean"].double() * s
+    Wf = sd["linear_fuse.conv.weight"].double().view(256, 1024)
+    proj, sizes = [], []
+    for i in range(4):
+        slot = 3 - i
+        Wfi = Wf[:, slot * 256:(slot + 1) * 256] * s[:, None]
+        pw = (Wfi @ sd[f"linear_c{i + 1}.proj.weight"].double()).float()
+        shift = shift + Wfi @ sd[f"linear_c{i + 1}.proj.bias"].double()
+        x = feats[i].permute(0, 2, 3, 1).reshape(-1, chans[i]).cuda().half()
+        p = torch.empty(x.shape[0], 256, dtype=torch.float16, device="cuda")
+        ops.gemm(x, pw.cuda().half(), out16=p)
+        proj.append(p)
+        sizes.append((h >> i, w >> i))
+    full = torch.empty(N * h * w, 256, dtype=torch.float16, device="cuda")
+    h32 = torch.empty(N * (h // 2) * (w // 2), 256, dtype=torch.float32, device="cuda")
+    h16_ = torch.empty(N * (h // 2) * (w // 2), 256, dtype=torch.float16, device="cuda")
+    ops.head_fuse(proj, sizes, N, 256, t_perm, shift.float().cuda(), c_full=full, half32=h32, half16=h16_)
+    if t_perm:                                     # clip-major in (n = b*T+t) -> frame-major out (t*B+b); B = 1 here
+        order = [(n % t_perm) * (N // t_perm) + n // t_perm for n in range(N)]
+        inv = torch.tensor(order).argsort()
+        c_ref, half_ref = c_ref[inv], half_ref[inv]
+    # fp16 projections feed a sum of 4 terms: 2e-3 of the output scale
+    check(full.view(N, h, w, 256), c_ref.permute(0, 2, 3, 1), 2e-3, "_c")
+    check(h32.view(N, h // 2, w // 2, 256), half_ref.permute(0, 2, 3, 1), 2e-3, "_c_further f32")
+    check(h16_.view(N, h // 2, w // 2, 256), half_ref.permute(0, 2, 3, 1), 2e-3, "_c_further f16")
+
+
+# ------------------------------------------------------------------------------------------- CFFA
+def _block_sd(seed):
+    spec = {"norm1.weight": (256,), "norm1.bias": (256,), "pool_layers.0.weight": (1, 49), "pool_layers.0.bias": (1,),
+            "pool_layers_clips.0.weight": (1, 49), "pool_layers_clips.0.bias": (1,),
+            "pool_layers_clips.1.weight": (1, 9), "pool_layers_clips.1.bias": (1,),
+            "pool_layers_clips.2.weight": (1, 4), "pool_layers_clips.2.bias": (1,)}
+    return synth.synth_state_dict({"blk." + k: v for k, v in spec.items()}, seed)
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 20, 25), (2, 14, 21), (1, 60, 60)])
+def test_cffa_norm_and_pool_vs_oracle(ops, B, H, W):
+    """LN + zero pad + (bilinear o fc-pool) == oracle cffa_assemble (cffm_transformer.py:713-805)."""
+    T, C = 4, 256
+    sd = _block_sd(21)
+    x = synth.synth_array((B, T, H, W, C), 22)                                    # clip-major for the oracle
+    xn_ref = F.layer_norm(x, (C,), sd["blk.norm1.weight"], sd["blk.norm1.bias"], 1e-5)
+    Hp, Wp = (H + 6) // 7 * 7, (W + 6) // 7 * 7
+    xn_pad = F.pad(xn_ref, (0, 0, 0, Wp - W, 0, Hp - H))
+    xfm = x.transpose(0, 1).contiguous().cuda()                                   # frame-major for the kernels
+    xn = torch.empty(T * B * H * W, C, dtype=torch.float16, device="cuda")
+    xt_pad = torch.zeros(B * Hp * Wp, C, dtype=torch.float16, device="cuda")
+    ops.cffa_norm(xfm, sd["blk.norm1.weight"].cuda(), sd["blk.norm1.bias"].cuda(), 1e-5, xn, xt_pad, B, T, H, W, Hp, Wp, C)
+    check(xn.view(T, B, H, W, C), xn_ref.transpose(0, 1), REL16, "norm1")
+    check(xt_pad.view(B, Hp, Wp, C), xn_pad[:, -1], REL16, "padded target")
+    assert xt_pad.view(B, Hp, Wp, C)[:, H:].abs().max().item() == 0 and xt_pad.view(B, Hp, Wp, C)[:, :, W:].abs().max().item() == 0
+    # pooling on the kernel's own fp16 LN output (isolates the pool kernel)
+    xn16 = xn.view(T, B, H, W, C).float().cpu().transpose(0, 1)
+    pooled_ref = O.cffa_assemble(sd, "blk", F.pad(xn16, (0, 0, 0, Wp - W, 0, Hp - H)))
+    pools = ["pool_layers.0", "pool_layers_clips.0", "pool_layers_clips.1", "pool_layers_clips.2"]
+    pw = torch.cat([sd[f"blk.{p}.weight"].reshape(-1) for p in pools]).cuda()
+    pb = torch.cat([sd[f"blk.{p}.bias"].reshape(-1) for p in pools]).cuda()
+    nW = (Hp // 7) * (Wp // 7)
+    pooled = torch.empty(B * 15 * nW, C, dtype=torch.float16, device="cuda")
+    ops.cffa_pool(xn, B, T, H, W, C, pw, pb, pooled)
+    got = pooled.view(B, 15 * nW, C)
+    off = 0
+    for lvl, pr in enumerate(pooled_ref):
+        n = pr.shape[1] * pr.shape[2]
+        check(got[:, off:off + n], pr.reshape(B, n, C), REL16, f"pooled level {lvl}")
+        off += n
+    assert off == 15 * nW
+
+
+# ------------------------------------------------------------------------------------ CFM attention
+@pytest.mark.parametrize("Hp,Wp", [(21, 28), (63, 63), (14, 14)])
+def test_cfm_key_sources_bit_exact(ops, golden_dir, Hp, Wp):
+    """In-kernel K/V source coordinates == oracle table == what the reference's roll / partition /
+    unfold / cat builds (golden key codes, cffm_transformer.py:378-522)."""
+    import os
+    got = ops.cfm_key_sources(Hp, Wp, "cuda").cpu().long()
+    lev, ys, xs = O.key_source_table(Hp, Wp)
+    assert torch.equal(got[..., 1], ys) and torch.equal(got[..., 2], xs)
+    assert torch.equal(torch.where(ys < 0, lev, got[..., 0]), lev)
+    t = np.load(os.path.join(golden_dir, "index_tables.npz"))
+    if f"key_code_{Hp}x{Wp}" in t:
+        code = torch.where(got[..., 1] < 0, torch.zeros_like(ys), got[..., 0] * 10000 + got[..., 1] * 100 + got[..., 2] + 1)
+        assert np.array_equal(code.to(torch.int32).numpy(), t[f"key_code_{Hp}x{Wp}"])
+
+
+def _attn_sd(golden_dir, seed):
+    import json, os
+    with open(os.path.join(golden_dir, "state_dict_spec.json")) as f:
+        spec = json.load(f)["b1"]
+    pre = "decode_head.decoder_focal.blocks.0.attn."
+    return {"attn." + k[len(pre):]: synth.synth_tensor("attn." + k[len(pre):], s, seed)
+            for k, s in spec.items() if k.startswith(pre) and not synth.is_derived_buffer(k)}
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 21, 28), (2, 20, 25), (1, 60, 60)])
+def test_cfm_attention_vs_oracle(ops, golden_dir, B, H, W):
+    """qkv GEMMs + CFM attention kernel == oracle cfm_attention before proj (cffm_transformer.py:364-601)."""
+    C, heads = 256, 8
+    Hp, Wp = (H + 6) // 7 * 7, (W + 6) // 7 * 7
+    nWh, nWw = Hp // 7, Wp // 7
+    nW = nWh * nWw
+    sd = _attn_sd(golden_dir, 3)
+    sd["attn.qkv.weight"], sd["attn.qkv.bias"] = h16(sd["attn.qkv.weight"]), sd["attn.qkv.bias"]
+    sd["attn.proj.weight"] = torch.eye(C)                                          # compare pre-proj
+    sd["attn.proj.bias"] = torch.zeros(C)
+    xt = h16(synth.synth_array((B, Hp, Wp, C), 11))
+    xt[:, H:] = 0; xt[:, :, W:] = 0                                               # zero pad after LN
+    pooled = [h16(synth.synth_array((B, nWh * l, nWw * l, C), 12 + i)) for i, l in enumerate((1, 1, 2, 3))]
+    ref = O.cfm_attention(sd, "attn", xt, pooled)                                  # (B*nW, 49, C)
+    ref = ref.view(B, nWh, nWw, 7, 7, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, C)[:, :H, :W]
+    qw, qb = sd["attn.qkv.weight"].cuda().half(), sd["attn.qkv.bias"].cuda()
+    qkv_t = torch.empty(B * Hp * Wp, 3 * C, dtype=torch.float16, device="cuda")
+    ops.gemm(xt.view(-1, C).cuda().half(), qw, bias=qb, out16=qkv_t)
+    pl = torch.cat([p.reshape(B, -1, C) for p in pooled], 1).reshape(-1, C).cuda().half()
+    kvp = torch.empty(B * 15 * nW, 2 * C, dtype=torch.float16, device="cuda")
+    ops.gemm(pl, qw[C:], bias=qb[C:], out16=kvp)
+    bias = tb.assemble_bias(sd["attn.relative_position_bias_table"].cuda(),
+                            sd["attn.relative_position_bias_table_to_neighbors"].cuda(),
+                            sd["attn.relative_position_bias_table_to_windows.0"].cuda(),
+                            [sd[f"attn.relative_position_bias_table_to_windows_clips.{k}"].cuda() for k in range(3)])
+    check(bias[:, :49, :289], O.cfm_bias_table(sd, "attn"), 0.0, "bias table (bit-exact gather)")
+    out = torch.empty(B * H * W, C, dtype=torch.float16, device="cuda")
+    ops.cfm_attention(qkv_t, kvp, bias, out, B, H, W, C, heads, (C // heads) ** -0.5)
+    # q, k, v are rounded to fp16 by the GEMM, P by the kernel: 3e-3 of the output scale
+    check(out.view(B, H, W, C), ref, 3e-3, "cfm attention")
+
+
+# ------------------------------------------------------------------------------------------- tails
+@pytest.mark.parametrize("f32in", [True, False])
+@pytest.mark.parametrize("B,h,w,Ho,Wo", [(2, 8, 12, 16, 24), (1, 60, 60, 120, 120), (2, 16, 24, 16, 24), (1, 5, 7, 13, 9)])
+def test_resize_nhwc_to_nchw(ops, f32in, B, h, w, Ho, Wo):
+    ncls, ldc = 124, 128
+    x = synth.synth_array((B, h, w, ldc), 31)
+    if not f32in:
+        x = h16(x)
+    ref = F.interpolate(x[..., :ncls].permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=False)
+    out = torch.empty(B, ncls, Ho, Wo, dtype=torch.float32, device="cuda")
+    ops.resize_nhwc_to_nchw(x.view(-1, ldc).cuda() if f32in else x.view(-1, ldc).cuda().half(), ncls, out, B, h, w, Ho, Wo)
+    check(out, ref, 1e-5, "resize nhwc->nchw")
+
+
+@pytest.mark.parametrize("B,C,h,w,Ho,Wo", [(2, 124, 16, 24, 64, 96), (1, 124, 120, 120, 480, 480), (1, 7, 9, 5, 20, 33)])
+def test_resize_nchw_softmax_argmax(ops, B, C, h, w, Ho, Wo):
+    x = synth.synth_array((B, C, h, w), 32)
+    up = F.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=False)
+    out = torch.empty(B, C, Ho, Wo, dtype=torch.float32, device="cuda")
+    ops.resize_nchw(x.cuda(), out)
+    check(out, up, 1e-5, "resize nchw")
+    sm = torch.empty_like(out)
+    ops.softmax_nchw(out, sm)
+    check(sm, torch.softmax(up, 1), 1e-5, "softmax")
+    labels = torch.empty(B, Ho, Wo, dtype=torch.int64, device="cuda")
+    ops.resize_argmax(x.cuda(), labels, B, C, h, w, Ho, Wo)
+    ref = torch.softmax(up, 1).argmax(1)                                       # reference order: resize, softmax, argmax
+    agree = (labels.cpu() == ref).float().mean().item()
+    assert agree >= 0.9999, agree                                               # fp32 near-ties may flip an fma rounding
+    top2 = up.topk(2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1])[labels.cpu() != ref]
+    assert margin.numel() == 0 or margin.max().item() < 1e-5

@@ -1,0 +1,542 @@
+// HBM-bound kernels of the CFFM path: LayerNorm, patch extraction, depthwise conv + GELU, the
+// folded MLP-decoder fuse, coarse-to-fine feature assembling (CFFA) and the bilinear tails.
+// All use 128-bit (8 x fp16 / 4 x fp32) accesses along the contiguous channel dimension.
+#include "common.cuh"
+
+namespace cffm {
+namespace {
+
+// PyTorch's align_corners=False source index (aten UpSample.h area_pixel_compute_source_index).
+struct Lerp {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ Lerp lerp_coord(int dst, float scale, int in_size) {
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  Lerp l;
+  l.i0 = min(static_cast<int>(src), in_size - 1);
+  l.i1 = l.i0 + (l.i0 < in_size - 1 ? 1 : 0);
+  l.w1 = src - static_cast<float>(l.i0);
+  l.w0 = 1.f - l.w1;
+  return l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row kept in registers (C <= 512), two-pass fp32 statistics.
+template <bool IN_F32>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const void* __restrict__ xin, int64_t ldx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __half* __restrict__ o16, int64_t ldo16,
+                 float* __restrict__ o32, int64_t ldo32, int M, int C) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  constexpr int MAXPL = 16;
+  float v[MAXPL];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXPL; ++i) {
+    const int c = lane + 32 * i;
+    float x = 0.f;
+    if (c < C) {
+      if (IN_F32) x = static_cast<const float*>(xin)[static_cast<int64_t>(row) * ldx + c];
+      else x = __half2float(static_cast<const __half*>(xin)[static_cast<int64_t>(row) * ldx + c]);
+    }
+    v[i] = x;
+    sum += x;
+  }
+  const float mean = warp_sum(sum) / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXPL; ++i) {
+    const int c = lane + 32 * i;
+    const float d = c < C ? v[i] - mean : 0.f;
+    sq += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXPL; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) {
+      const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      if (o16) o16[static_cast<int64_t>(row) * ldo16 + c] = __float2half_rn(y);
+      if (o32) o32[static_cast<int64_t>(row) * ldo32 + c] = y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col, K order (ky, kx, c)
+__global__ void __launch_bounds__(256)
+im2col_nhwc_kernel(const __half* __restrict__ x, int N, int H, int W, int C, int k, int stride, int pad, int Ho,
+                   int Wo, __half* __restrict__ A, int Kpad) {
+  const int chunks = Kpad / 8;
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * chunks;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int ch = static_cast<int>(i % chunks);
+    const int64_t m = i / chunks;
+    const int kcol = ch * 8;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (kcol < k * k * C) {
+      const int tap = kcol / C, c = kcol % C;
+      const int ky = tap / k, kx = tap % k;
+      const int ox = static_cast<int>(m % Wo), oy = static_cast<int>((m / Wo) % Ho), n = static_cast<int>(m / (Wo * Ho));
+      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+        val = *reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * C + c);
+    }
+    *reinterpret_cast<uint4*>(A + m * Kpad + kcol) = val;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+im2col_nchw_f32_kernel(const float* __restrict__ x, int N, int H, int W, int C, int k, int stride, int pad, int Ho,
+                       int Wo, __half* __restrict__ A, int Kpad) {
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * Kpad;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int kcol = static_cast<int>(i % Kpad);
+    const int64_t m = i / Kpad;
+    float val = 0.f;
+    if (kcol < k * k * C) {
+      const int tap = kcol / C, c = kcol % C;
+      const int ky = tap / k, kx = tap % k;
+      const int ox = static_cast<int>(m % Wo), oy = static_cast<int>((m / Wo) % Ho), n = static_cast<int>(m / (Wo * Ho));
+      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = x[((static_cast<int64_t>(n) * C + c) * H + iy) * W + ix];
+    }
+    A[i] = __float2half_rn(val);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3 (pad 1) + bias + GELU, NHWC fp16, 8 channels per thread
+__global__ void __launch_bounds__(256)
+dwconv3x3_gelu_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
+                      __half* __restrict__ out, int N, int H, int W, int C) {
+  const int chunks = C / 8;
+  const int64_t total = static_cast<int64_t>(N) * H * W * chunks;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int c = static_cast<int>(i % chunks) * 8;
+    const int64_t p = i / chunks;
+    const int xx = static_cast<int>(p % W), yy = static_cast<int>((p / W) % H), n = static_cast<int>(p / (W * H));
+    float acc[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = yy + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = xx + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        float xv[8], wv[8];
+        unpack8(*reinterpret_cast<const half8*>(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * C + c), xv);
+        unpack8(*reinterpret_cast<const half8*>(w + (ky * 3 + kx) * C + c), wv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(xv[e], wv[e], acc[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = gelu_erf(acc[e]);
+    *reinterpret_cast<half8*>(out + p * C + c) = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// c = relu(p1 + up(p2) + up(p3) + up(p4) + shift); optional full-res fp16 copy; 2x2 mean outputs.
+__device__ __forceinline__ void add_bilerp(float* acc, const __half* __restrict__ p, int n, int Hs, int Ws, int C,
+                                           int c, const Lerp& ly, const Lerp& lx) {
+  const __half* base = p + static_cast<int64_t>(n) * Hs * Ws * C + c;
+  float t[8];
+  unpack8(*reinterpret_cast<const half8*>(base + (static_cast<int64_t>(ly.i0) * Ws + lx.i0) * C), t);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = fmaf(ly.w0 * lx.w0, t[e], acc[e]);
+  unpack8(*reinterpret_cast<const half8*>(base + (static_cast<int64_t>(ly.i0) * Ws + lx.i1) * C), t);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = fmaf(ly.w0 * lx.w1, t[e], acc[e]);
+  unpack8(*reinterpret_cast<const half8*>(base + (static_cast<int64_t>(ly.i1) * Ws + lx.i0) * C), t);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = fmaf(ly.w1 * lx.w0, t[e], acc[e]);
+  unpack8(*reinterpret_cast<const half8*>(base + (static_cast<int64_t>(ly.i1) * Ws + lx.i1) * C), t);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = fmaf(ly.w1 * lx.w1, t[e], acc[e]);
+}
+
+__global__ void __launch_bounds__(256)
+head_fuse_kernel(const __half* __restrict__ p1, const __half* __restrict__ p2, const __half* __restrict__ p3,
+                 const __half* __restrict__ p4, int N, int H1, int W1, int H2, int W2, int H3, int W3, int H4, int W4,
+                 int C, int Tperm, const float* __restrict__ shift, __half* __restrict__ c_full,
+                 float* __restrict__ h32, int64_t ldh32, __half* __restrict__ h16, int64_t ldh16) {
+  const int chunks = C / 8, Hh = H1 / 2, Wh = W1 / 2;
+  const int64_t total = static_cast<int64_t>(N) * Hh * Wh * chunks;
+  const float sy2 = static_cast<float>(H2) / H1, sx2 = static_cast<float>(W2) / W1;
+  const float sy3 = static_cast<float>(H3) / H1, sx3 = static_cast<float>(W3) / W1;
+  const float sy4 = static_cast<float>(H4) / H1, sx4 = static_cast<float>(W4) / W1;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int c = static_cast<int>(i % chunks) * 8;
+    const int64_t p = i / chunks;
+    const int xh = static_cast<int>(p % Wh), yh = static_cast<int>((p / Wh) % Hh), n = static_cast<int>(p / (Wh * Hh));
+    // input frame n = b*T + t (reference order) -> output slot t*B + b (frame-major, targets last)
+    const int no = Tperm > 1 ? (n % Tperm) * (N / Tperm) + n / Tperm : n;
+    const int64_t po = (static_cast<int64_t>(no) * Hh + yh) * Wh + xh;
+    float sh[8], mean[8];
+    {
+      const float4 s0 = *reinterpret_cast<const float4*>(shift + c), s1 = *reinterpret_cast<const float4*>(shift + c + 4);
+      sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mean[e] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int y = 2 * yh + dy;
+      const Lerp ly2 = lerp_coord(y, sy2, H2), ly3 = lerp_coord(y, sy3, H3), ly4 = lerp_coord(y, sy4, H4);
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int x = 2 * xh + dx;
+        float acc[8];
+        const int64_t pix = (static_cast<int64_t>(n) * H1 + y) * W1 + x;
+        unpack8(*reinterpret_cast<const half8*>(p1 + pix * C + c), acc);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += sh[e];
+        add_bilerp(acc, p2, n, H2, W2, C, c, ly2, lerp_coord(x, sx2, W2));
+        add_bilerp(acc, p3, n, H3, W3, C, c, ly3, lerp_coord(x, sx3, W3));
+        add_bilerp(acc, p4, n, H4, W4, C, c, ly4, lerp_coord(x, sx4, W4));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { acc[e] = fmaxf(acc[e], 0.f); mean[e] += acc[e]; }
+        if (c_full)
+          *reinterpret_cast<half8*>(c_full + ((static_cast<int64_t>(no) * H1 + y) * W1 + x) * C + c) = pack8(acc);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mean[e] *= 0.25f;
+    if (h32) {
+      float* o = h32 + po * ldh32 + c;
+      *reinterpret_cast<float4*>(o) = make_float4(mean[0], mean[1], mean[2], mean[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(mean[4], mean[5], mean[6], mean[7]);
+    }
+    if (h16) *reinterpret_cast<half8*>(h16 + po * ldh16 + c) = pack8(mean);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CFFA norm: LN over C = 256 of every frame; one warp per token, 8 channels per lane.
+__global__ void __launch_bounds__(256)
+cffa_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 float eps, __half* __restrict__ xn, __half* __restrict__ xt_pad, int B, int T, int H, int W, int Hp,
+                 int Wp) {
+  constexpr int C = 256;
+  const int64_t tok = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tok >= static_cast<int64_t>(B) * T * H * W) return;
+  const float* px = x + tok * C + lane * 8;
+  const float4 a = *reinterpret_cast<const float4*>(px), b = *reinterpret_cast<const float4*>(px + 4);
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s += v[e];
+  const float mean = warp_sum(s) * (1.f / C);
+  float sq = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { v[e] -= mean; sq += v[e] * v[e]; }
+  const float rstd = rsqrtf(warp_sum(sq) * (1.f / C) + eps);
+  const float4 g0 = *reinterpret_cast<const float4*>(gamma + lane * 8), g1 = *reinterpret_cast<const float4*>(gamma + lane * 8 + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(beta + lane * 8), b1 = *reinterpret_cast<const float4*>(beta + lane * 8 + 4);
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = v[e] * rstd * gg[e] + bb[e];
+  const half8 o = pack8(v);
+  *reinterpret_cast<half8*>(xn + tok * C + lane * 8) = o;
+  const int xx = static_cast<int>(tok % W), yy = static_cast<int>((tok / W) % H);
+  const int frame = static_cast<int>(tok / (static_cast<int64_t>(W) * H));   // frame-major: frame = t*B + b
+  const int bi = frame - (T - 1) * B;
+  if (bi >= 0)
+    *reinterpret_cast<half8*>(xt_pad + ((static_cast<int64_t>(bi) * Hp + yy) * Wp + xx) * C + lane * 8) = o;
+}
+
+// CFFA pooling: one warp per pooled token. Levels: 0 target 7x7 | 1 ref0 7x7 | 2 ref1 resize+3x3 | 3 ref2 resize+2x2
+__global__ void __launch_bounds__(256)
+cffa_pool_kernel(const __half* __restrict__ xn, int B, int T, int H, int W, int Hp, int Wp,
+                 const float* __restrict__ pool_w, const float* __restrict__ pool_b, __half* __restrict__ pooled) {
+  constexpr int C = 256, WS = 7;
+  const int nWh = Hp / WS, nWw = Wp / WS, nW = nWh * nWw, P = 15 * nW;
+  const int64_t gw = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= static_cast<int64_t>(B) * P) return;
+  const int b = static_cast<int>(gw / P);
+  int pos = static_cast<int>(gw % P);
+  int level, frame, wg, gwid, woff;
+  if (pos < nW) { level = 0; frame = T - 1; wg = 7; gwid = nWw; woff = 0; }
+  else if (pos < 2 * nW) { level = 1; pos -= nW; frame = 0; wg = 7; gwid = nWw; woff = 49; }
+  else if (pos < 6 * nW) { level = 2; pos -= 2 * nW; frame = 1; wg = 3; gwid = 2 * nWw; woff = 98; }
+  else { level = 3; pos -= 6 * nW; frame = 2; wg = 2; gwid = 3 * nWw; woff = 107; }
+  const int py = pos / gwid, px = pos % gwid;
+  const __half* src = xn + (static_cast<int64_t>(frame) * B + b) * H * W * C + lane * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (level < 2) {                                            // 7x7 fc-pool on the zero-padded map itself
+    for (int u = 0; u < WS; ++u) {
+      const int y = WS * py + u;
+      if (y >= H) break;
+      for (int v = 0; v < WS; ++v) {
+        const int xx = WS * px + v;
+        if (xx >= W) break;
+        const float wt = pool_w[woff + u * WS + v];
+        float t[8];
+        unpack8(*reinterpret_cast<const half8*>(src + (static_cast<int64_t>(y) * W + xx) * C), t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wt, t[e], acc[e]);
+      }
+    }
+  } else {                                                    // bilinear (Hp,Wp)->(Hpool,Wpool) then wg x wg fc-pool
+    const int Hpool = nWh * 6, Wpool = nWw * 6;                     // l * floor(7/l) = 2*3 = 3*2 = 6 rows per window
+    const float sy = static_cast<float>(Hp) / Hpool, sx = static_cast<float>(Wp) / Wpool;
+    for (int u = 0; u < wg; ++u) {
+      const Lerp ly = lerp_coord(wg * py + u, sy, Hp);
+      for (int v = 0; v < wg; ++v) {
+        const Lerp lx = lerp_coord(wg * px + v, sx, Wp);
+        const float wt = pool_w[woff + u * wg + v];
+        const int ys[2] = {ly.i0, ly.i1}, xs[2] = {lx.i0, lx.i1};
+        const float wy[2] = {ly.w0, ly.w1}, wx[2] = {lx.w0, lx.w1};
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int bq = 0; bq < 2; ++bq) {
+            if (ys[a] < H && xs[bq] < W) {                    // pad rows/cols of the LN'ed map are zero
+              float t[8];
+              unpack8(*reinterpret_cast<const half8*>(src + (static_cast<int64_t>(ys[a]) * W + xs[bq]) * C), t);
+              const float ww = wt * wy[a] * wx[bq];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[e] = fmaf(ww, t[e], acc[e]);
+            }
+          }
+      }
+    }
+  }
+  const float pb = pool_b[level];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] += pb;
+  *reinterpret_cast<half8*>(pooled + gw * C + lane * 8) = pack8(acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool IN_F32>
+__global__ void __launch_bounds__(256)
+resize_nhwc_to_nchw_kernel(const void* __restrict__ in, int64_t ldc, float* __restrict__ out, int B, int h, int w,
+                           int ncls, int Ho, int Wo) {
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo;
+  const float sy = static_cast<float>(h) / Ho, sx = static_cast<float>(w) / Wo;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int X = static_cast<int>(i % Wo), Y = static_cast<int>((i / Wo) % Ho), b = static_cast<int>(i / (static_cast<int64_t>(Wo) * Ho));
+    const Lerp ly = lerp_coord(Y, sy, h), lx = lerp_coord(X, sx, w);
+    const int64_t r00 = ((static_cast<int64_t>(b) * h + ly.i0) * w + lx.i0) * ldc, r01 = ((static_cast<int64_t>(b) * h + ly.i0) * w + lx.i1) * ldc;
+    const int64_t r10 = ((static_cast<int64_t>(b) * h + ly.i1) * w + lx.i0) * ldc, r11 = ((static_cast<int64_t>(b) * h + ly.i1) * w + lx.i1) * ldc;
+    for (int c = 0; c < ncls; ++c) {
+      float v00, v01, v10, v11;
+      if (IN_F32) {
+        const float* p = static_cast<const float*>(in);
+        v00 = p[r00 + c]; v01 = p[r01 + c]; v10 = p[r10 + c]; v11 = p[r11 + c];
+      } else {
+        const __half* p = static_cast<const __half*>(in);
+        v00 = __half2float(p[r00 + c]); v01 = __half2float(p[r01 + c]);
+        v10 = __half2float(p[r10 + c]); v11 = __half2float(p[r11 + c]);
+      }
+      // same association as aten: w0y*(w0x*a + w1x*b) + w1y*(w0x*c + w1x*d)
+      const float v = ly.w0 * (lx.w0 * v00 + lx.w1 * v01) + ly.w1 * (lx.w0 * v10 + lx.w1 * v11);
+      out[((static_cast<int64_t>(b) * ncls + c) * Ho + Y) * Wo + X] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+resize_argmax_kernel(const float* __restrict__ logits, int64_t* __restrict__ labels, int B, int ncls, int h, int w,
+                     int Ho, int Wo) {
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo;
+  const float sy = static_cast<float>(h) / Ho, sx = static_cast<float>(w) / Wo;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int X = static_cast<int>(i % Wo), Y = static_cast<int>((i / Wo) % Ho), b = static_cast<int>(i / (static_cast<int64_t>(Wo) * Ho));
+    const Lerp ly = lerp_coord(Y, sy, h), lx = lerp_coord(X, sx, w);
+    const float* base = logits + static_cast<int64_t>(b) * ncls * h * w;
+    const int o00 = ly.i0 * w + lx.i0, o01 = ly.i0 * w + lx.i1, o10 = ly.i1 * w + lx.i0, o11 = ly.i1 * w + lx.i1;
+    float best = -INFINITY;
+    int arg = 0;
+    for (int c = 0; c < ncls; ++c) {
+      const float* p = base + static_cast<int64_t>(c) * h * w;
+      const float v = ly.w0 * (lx.w0 * p[o00] + lx.w1 * p[o01]) + ly.w1 * (lx.w0 * p[o10] + lx.w1 * p[o11]);
+      if (v > best) { best = v; arg = c; }
+    }
+    labels[i] = arg;
+  }
+}
+
+// plain fp32 NCHW -> NCHW bilinear resize (whole_inference rescale step)
+__global__ void __launch_bounds__(256)
+resize_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t planes, int h, int w, int Ho, int Wo) {
+  const int64_t total = planes * Ho * Wo;
+  const float sy = static_cast<float>(h) / Ho, sx = static_cast<float>(w) / Wo;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int X = static_cast<int>(i % Wo), Y = static_cast<int>((i / Wo) % Ho);
+    const int64_t pl = i / (static_cast<int64_t>(Wo) * Ho);
+    const Lerp ly = lerp_coord(Y, sy, h), lx = lerp_coord(X, sx, w);
+    const float* p = in + pl * h * w;
+    out[i] = ly.w0 * (lx.w0 * p[ly.i0 * w + lx.i0] + lx.w1 * p[ly.i0 * w + lx.i1]) +
+             ly.w1 * (lx.w0 * p[ly.i1 * w + lx.i0] + lx.w1 * p[ly.i1 * w + lx.i1]);
+  }
+}
+
+// softmax over the channel dimension of fp32 NCHW; one thread per pixel (coalesced along W)
+__global__ void __launch_bounds__(256)
+softmax_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int64_t HW) {
+  const int64_t total = static_cast<int64_t>(B) * HW;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int64_t b = i / HW, px = i % HW;
+    const float* p = in + b * C * HW + px;
+    float* o = out + b * C * HW + px;
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, p[c * HW]);
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) sum += expf(p[c * HW] - m);
+    const float inv = 1.f / sum;
+    for (int c = 0; c < C; ++c) o[c * HW] = expf(p[c * HW] - m) * inv;
+  }
+}
+
+inline int grid_for(int64_t work_items, int per_block = 256) {
+  int64_t g = (work_items + per_block - 1) / per_block;
+  const int64_t cap = 148 * 16;                               // grid-stride: a few waves over 148 SMs
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+}  // namespace cffm
+
+using namespace cffm;
+
+extern "C" int cffm_layernorm(const void* x, int x_is_f32, int64_t ldx, const float* gamma, const float* beta,
+                              float eps, void* out_f16, int64_t ldo16, float* out_f32, int64_t ldo32, int M, int C,
+                              void* stream) {
+  CFFM_REQUIRE(x && gamma && beta && (out_f16 || out_f32), CFFM_E_BADARG, "layernorm: null pointer");
+  CFFM_REQUIRE(M > 0 && C > 0, CFFM_E_BADARG, "layernorm: non-positive size");
+  CFFM_REQUIRE(C <= 512, CFFM_E_UNSUPPORTED, "layernorm: C=%d > 512", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (M + 7) / 8;
+  if (x_is_f32)
+    layernorm_kernel<true><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, static_cast<__half*>(out_f16), ldo16,
+                                                 out_f32, ldo32, M, C);
+  else
+    layernorm_kernel<false><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, static_cast<__half*>(out_f16), ldo16,
+                                                  out_f32, ldo32, M, C);
+  return launch_status("layernorm_kernel");
+}
+
+extern "C" int cffm_im2col(const void* x, int layout, int N, int H, int W, int C, int k, int stride, int pad, void* A,
+                           int Kpad, void* stream) {
+  CFFM_REQUIRE(x && A, CFFM_E_BADARG, "im2col: null pointer");
+  CFFM_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0, CFFM_E_BADARG, "im2col: bad size");
+  CFFM_REQUIRE(Kpad >= k * k * C && Kpad % 8 == 0, CFFM_E_BADARG, "im2col: Kpad=%d must be >= k*k*C and %% 8 == 0", Kpad);
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  CFFM_REQUIRE(Ho > 0 && Wo > 0, CFFM_E_BADARG, "im2col: empty output");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (layout == 1) {
+    CFFM_REQUIRE(C % 8 == 0 && aligned16(x) && aligned16(A), CFFM_E_UNSUPPORTED, "im2col: NHWC path needs C %% 8 == 0");
+    im2col_nhwc_kernel<<<grid_for(static_cast<int64_t>(N) * Ho * Wo * (Kpad / 8)), 256, 0, st>>>(
+        static_cast<const __half*>(x), N, H, W, C, k, stride, pad, Ho, Wo, static_cast<__half*>(A), Kpad);
+  } else {
+    CFFM_REQUIRE(layout == 0, CFFM_E_BADARG, "im2col: bad layout %d", layout);
+    im2col_nchw_f32_kernel<<<grid_for(static_cast<int64_t>(N) * Ho * Wo * Kpad), 256, 0, st>>>(
+        static_cast<const float*>(x), N, H, W, C, k, stride, pad, Ho, Wo, static_cast<__half*>(A), Kpad);
+  }
+  return launch_status("im2col_kernel");
+}
+
+extern "C" int cffm_dwconv3x3_gelu(const void* x, const void* w, const float* bias, void* out, int N, int H, int W,
+                                   int C, void* stream) {
+  CFFM_REQUIRE(x && w && bias && out, CFFM_E_BADARG, "dwconv: null pointer");
+  CFFM_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, CFFM_E_UNSUPPORTED, "dwconv: need C %% 8 == 0");
+  CFFM_REQUIRE(aligned16(x) && aligned16(w) && aligned16(bias) && aligned16(out), CFFM_E_BADARG, "dwconv: misaligned");
+  dwconv3x3_gelu_kernel<<<grid_for(static_cast<int64_t>(N) * H * W * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<const __half*>(w), bias, static_cast<__half*>(out), N, H, W, C);
+  return launch_status("dwconv3x3_gelu_kernel");
+}
+
+extern "C" int cffm_head_fuse(const void* p1, const void* p2, const void* p3, const void* p4, int N, int H1, int W1,
+                              int H2, int W2, int H3, int W3, int H4, int W4, int C, int T_perm, const float* shift,
+                              void* c_full, float* c_half_f32, int64_t ldh32, void* c_half_f16, int64_t ldh16,
+                              void* stream) {
+  CFFM_REQUIRE(p1 && p2 && p3 && p4 && shift, CFFM_E_BADARG, "head_fuse: null pointer");
+  CFFM_REQUIRE(c_full || c_half_f32 || c_half_f16, CFFM_E_BADARG, "head_fuse: no output requested");
+  CFFM_REQUIRE(N > 0 && H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && H3 > 0 && W3 > 0 && H4 > 0 && W4 > 0, CFFM_E_BADARG,
+               "head_fuse: non-positive size");
+  CFFM_REQUIRE(C % 8 == 0 && H1 % 2 == 0 && W1 % 2 == 0, CFFM_E_UNSUPPORTED, "head_fuse: need C %% 8 == 0 and even H1, W1");
+  CFFM_REQUIRE((!c_half_f32 || ldh32 % 4 == 0) && (!c_half_f16 || ldh16 % 8 == 0), CFFM_E_BADARG, "head_fuse: bad stride");
+  CFFM_REQUIRE(T_perm >= 0 && (T_perm <= 1 || N % T_perm == 0), CFFM_E_BADARG, "head_fuse: N=%d not a multiple of T_perm=%d", N, T_perm);
+  head_fuse_kernel<<<grid_for(static_cast<int64_t>(N) * (H1 / 2) * (W1 / 2) * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(p1), static_cast<const __half*>(p2), static_cast<const __half*>(p3),
+      static_cast<const __half*>(p4), N, H1, W1, H2, W2, H3, W3, H4, W4, C, T_perm, shift, static_cast<__half*>(c_full),
+      c_half_f32, ldh32, static_cast<__half*>(c_half_f16), ldh16);
+  return launch_status("head_fuse_kernel");
+}
+
+extern "C" int cffm_cffa_norm(const float* x, const float* gamma, const float* beta, float eps, void* xn, void* xt_pad,
+                              int B, int T, int H, int W, int Hp, int Wp, int C, void* stream) {
+  CFFM_REQUIRE(x && gamma && beta && xn && xt_pad, CFFM_E_BADARG, "cffa_norm: null pointer");
+  CFFM_REQUIRE(B > 0 && T > 0 && H > 0 && W > 0 && Hp >= H && Wp >= W, CFFM_E_BADARG, "cffa_norm: bad size");
+  CFFM_REQUIRE(C == 256, CFFM_E_UNSUPPORTED, "cffa_norm: built for C=256, got %d", C);
+  const int64_t tokens = static_cast<int64_t>(B) * T * H * W;
+  cffa_norm_kernel<<<static_cast<int>((tokens + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, gamma, beta, eps, static_cast<__half*>(xn), static_cast<__half*>(xt_pad), B, T, H, W, Hp, Wp);
+  return launch_status("cffa_norm_kernel");
+}
+
+extern "C" int cffm_cffa_pool(const void* xn, int B, int T, int H, int W, int C, const float* pool_w,
+                              const float* pool_b, void* pooled, void* stream) {
+  CFFM_REQUIRE(xn && pool_w && pool_b && pooled, CFFM_E_BADARG, "cffa_pool: null pointer");
+  CFFM_REQUIRE(B > 0 && H > 0 && W > 0, CFFM_E_BADARG, "cffa_pool: bad size");
+  CFFM_REQUIRE(C == 256 && T == 4, CFFM_E_UNSUPPORTED,
+               "cffa_pool: built for C=256 and T=4 (3 reference frames, focal_l_clips=[1,2,3]); got C=%d T=%d", C, T);
+  const int Hp = (H + 6) / 7 * 7, Wp = (W + 6) / 7 * 7;
+  const int64_t warps = static_cast<int64_t>(B) * 15 * (Hp / 7) * (Wp / 7);
+  cffa_pool_kernel<<<static_cast<int>((warps + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(xn), B, T, H, W, Hp, Wp, pool_w, pool_b, static_cast<__half*>(pooled));
+  return launch_status("cffa_pool_kernel");
+}
+
+extern "C" int cffm_resize_nhwc_to_nchw(const void* in, int in_is_f32, int64_t ldc, float* out, int B, int h, int w,
+                                        int ncls, int Ho, int Wo, void* stream) {
+  CFFM_REQUIRE(in && out, CFFM_E_BADARG, "resize: null pointer");
+  CFFM_REQUIRE(B > 0 && h > 0 && w > 0 && ncls > 0 && Ho > 0 && Wo > 0 && ldc >= ncls, CFFM_E_BADARG, "resize: bad size");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(static_cast<int64_t>(B) * Ho * Wo);
+  if (in_is_f32) resize_nhwc_to_nchw_kernel<true><<<grid, 256, 0, st>>>(in, ldc, out, B, h, w, ncls, Ho, Wo);
+  else resize_nhwc_to_nchw_kernel<false><<<grid, 256, 0, st>>>(in, ldc, out, B, h, w, ncls, Ho, Wo);
+  return launch_status("resize_nhwc_to_nchw_kernel");
+}
+
+extern "C" int cffm_resize_argmax(const float* logits, int64_t* labels, int B, int ncls, int h, int w, int Ho, int Wo,
+                                  void* stream) {
+  CFFM_REQUIRE(logits && labels, CFFM_E_BADARG, "resize_argmax: null pointer");
+  CFFM_REQUIRE(B > 0 && ncls > 0 && h > 0 && w > 0 && Ho > 0 && Wo > 0, CFFM_E_BADARG, "resize_argmax: bad size");
+  resize_argmax_kernel<<<grid_for(static_cast<int64_t>(B) * Ho * Wo), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, labels, B, ncls, h, w, Ho, Wo);
+  return launch_status("resize_argmax_kernel");
+}
+
+extern "C" int cffm_resize_nchw(const float* in, float* out, int B, int C, int h, int w, int Ho, int Wo, void* stream) {
+  CFFM_REQUIRE(in && out, CFFM_E_BADARG, "resize_nchw: null pointer");
+  CFFM_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0 && Ho > 0 && Wo > 0, CFFM_E_BADARG, "resize_nchw: bad size");
+  const int64_t planes = static_cast<int64_t>(B) * C;
+  resize_nchw_kernel<<<grid_for(planes * Ho * Wo), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, planes, h, w, Ho, Wo);
+  return launch_status("resize_nchw_kernel");
+}
+
+extern "C" int cffm_softmax_nchw(const float* in, float* out, int B, int C, int64_t HW, void* stream) {
+  CFFM_REQUIRE(in && out, CFFM_E_BADARG, "softmax_nchw: null pointer");
+  CFFM_REQUIRE(B > 0 && C > 0 && HW > 0, CFFM_E_BADARG, "softmax_nchw: bad size");
+  softmax_nchw_kernel<<<grid_for(static_cast<int64_t>(B) * HW), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, B, C, HW);
+  return launch_status("softmax_nchw_kernel");
+}

@@ -1,0 +1,309 @@
+// out = act(A . W^T + bias) (+ residual) on the 5th-generation tensor cores.
+//
+// One 128 x BN output tile per CTA.  Warp-specialised:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzled [rows][64] fp16 stages)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (accumulator in TMEM)
+//   warps 2..5  epilogue       (tcgen05.ld -> bias / GELU / ReLU / fp32 residual -> global)
+// Stage ring: full[s] (TMA -> MMA, transaction bytes) / empty[s] (tcgen05.commit -> TMA).
+// Two CTAs fit per SM (<= 97 KB smem, <= 128 TMEM columns each), so one CTA's epilogue
+// overlaps the other's main loop.  Tails in M, N and K are handled by TMA out-of-bounds
+// zero fill plus predicated stores.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace cffm {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                       // 64 halves = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+struct Epilogue {
+  const float* bias;
+  const float* residual;
+  int64_t ldr;
+  __half* out16;
+  int64_t ldo16;
+  float* out32;
+  int64_t ldo32;
+  int act;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = (BN == 64) ? 4 : 3;
+  static constexpr int W_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + W_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == CFFM_ACT_GELU) return gelu_erf(x);
+  if (act == CFFM_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const Epilogue ep, const int M, const int N, const int K) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  uint8_t* smem = smem_raw + pad;                              // 1024-byte aligned (SWIZZLE_128B atom)
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + C::STAGES * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BLOCK_M;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmW);
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {                                             // whole warp: .sync.aligned
+    ptx::tmem_alloc(tmem_base_smem, BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % C::STAGES;
+        const uint32_t ph = (kb / C::STAGES) & 1;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);                // slot free (passes on the first round)
+        ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+        ptx::tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BLOCK_K, m0);
+        ptx::tma_load_2d(sW + s * C::W_STAGE_BYTES, &tmW, &full_bar[s], kb * BLOCK_K, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer (one thread) =====================
+      constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % C::STAGES;
+        const uint32_t ph = (kb / C::STAGES) & 1;
+        ptx::mbar_wait(&full_bar[s], ph);                      // TMA bytes have landed
+        ptx::tc_fence_after();
+        const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(sA + s * A_STAGE_BYTES));
+        const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(sW + s * C::W_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advance 16 halves = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+          ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[s]);                       // frees the smem slot when the MMAs retire
+      }
+      ptx::umma_commit(tmem_full_bar);                         // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    const int wq = warp & 3;                                   // TMEM lane quarter this warp may access
+    const int row = m0 + wq * 32 + lane;
+    const bool row_ok = row < M;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;                                 // warp-uniform
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + c0, v);
+      ptx::tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = n0 + c0 + j * 8;
+          if (col < N) {                                       // N % 8 == 0: whole 8-wide chunk valid
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
+            if (ep.bias != nullptr) {
+              const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + col);
+              const float4 b1 = *reinterpret_cast<const float4*>(ep.bias + col + 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (ep.act != CFFM_ACT_NONE) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = apply_act(f[e], ep.act);
+            }
+            if (ep.residual != nullptr) {
+              const float* r = ep.residual + static_cast<int64_t>(row) * ep.ldr + col;
+              const float4 r0 = *reinterpret_cast<const float4*>(r);
+              const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
+              f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+              f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+            }
+            if (ep.out32 != nullptr) {
+              float* o = ep.out32 + static_cast<int64_t>(row) * ep.ldo32 + col;
+              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            }
+            if (ep.out16 != nullptr) {
+              *reinterpret_cast<half8*>(ep.out16 + static_cast<int64_t>(row) * ep.ldo16 + col) = pack8(f);
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, BN);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Cross-check kernel (tests / bring-up only): plain CUDA-core tiled GEMM, same epilogue semantics.
+constexpr int CK_T = 64;
+__global__ void __launch_bounds__(256)
+gemm_check_kernel(const __half* __restrict__ A, int64_t lda, const __half* __restrict__ W, int64_t ldw,
+                  const Epilogue ep, int M, int N, int K) {
+  __shared__ float sA[16][CK_T + 1];
+  __shared__ float sW[16][CK_T + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * CK_T, n0 = blockIdx.x * CK_T;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < CK_T * 16; i += 256) {
+      const int r = i >> 4, c = i & 15;
+      const int gm = m0 + r, gn = n0 + r, gk = k0 + c;
+      sA[c][r] = (gm < M && gk < K) ? __half2float(A[static_cast<int64_t>(gm) * lda + gk]) : 0.f;
+      sW[c][r] = (gn < N && gk < K) ? __half2float(W[static_cast<int64_t>(gn) * ldw + gk]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[k][ty * 4 + i]; b[i] = sW[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < M && n < N) {
+        float f = acc[i][j] + (ep.bias ? ep.bias[n] : 0.f);
+        f = apply_act(f, ep.act);
+        if (ep.residual) f += ep.residual[static_cast<int64_t>(m) * ep.ldr + n];
+        if (ep.out32) ep.out32[static_cast<int64_t>(m) * ep.ldo32 + n] = f;
+        if (ep.out16) ep.out16[static_cast<int64_t>(m) * ep.ldo16 + n] = __float2half_rn(f);
+      }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D fp16 row-major [rows, K] with row stride ld (elements); box = [box_rows][64], 128-byte swizzle.
+int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  CFFM_REQUIRE(fn != nullptr, CFFM_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CFFM_REQUIRE(r == CUDA_SUCCESS, CFFM_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld K=%lld ld=%lld)",
+               static_cast<int>(r), (long long)rows, (long long)K, (long long)ld);
+  return CFFM_OK;
+}
+
+template <int BN>
+int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const Epilogue& ep, int M, int N, int K,
+                   cudaStream_t st) {
+  CUtensorMap tmA, tmW;
+  int rc = make_tmap(&tmA, A, M, K, lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap(&tmW, W, N, K, ldw, BN);
+  if (rc) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg<BN>::SMEM_BYTES);
+  });
+  CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  dim3 grid((N + BN - 1) / BN, (M + BLOCK_M - 1) / BLOCK_M);
+  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmW, ep, M, N, K);
+  return launch_status("gemm_tcgen05_kernel");
+}
+
+}  // namespace
+}  // namespace cffm
+
+extern "C" int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                             const float* residual, int64_t ldr, void* out_f16, int64_t ldo16, float* out_f32,
+                             int64_t ldo32, int M, int N, int K, int act, int impl, void* stream) {
+  using namespace cffm;
+  CFFM_REQUIRE(A && W && (out_f16 || out_f32), CFFM_E_BADARG, "gemm: null operand");
+  CFFM_REQUIRE(M > 0 && N > 0 && K > 0, CFFM_E_BADARG, "gemm: non-positive size M=%d N=%d K=%d", M, N, K);
+  CFFM_REQUIRE(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, CFFM_E_UNSUPPORTED,
+               "gemm: need K,N,lda,ldw multiples of 8 (M=%d N=%d K=%d lda=%lld ldw=%lld)", M, N, K, (long long)lda,
+               (long long)ldw);
+  CFFM_REQUIRE(aligned16(A) && aligned16(W) && aligned16(bias) && aligned16(residual) && aligned16(out_f16) &&
+                   aligned16(out_f32),
+               CFFM_E_BADARG, "gemm: pointers must be 16-byte aligned");
+  CFFM_REQUIRE((!out_f16 || (ldo16 % 8 == 0 && ldo16 >= N)) && (!out_f32 || (ldo32 % 4 == 0 && ldo32 >= N)) &&
+                   (!residual || (ldr % 4 == 0 && ldr >= N)),
+               CFFM_E_BADARG, "gemm: bad output/residual stride");
+  CFFM_REQUIRE(act >= CFFM_ACT_NONE && act <= CFFM_ACT_RELU, CFFM_E_BADARG, "gemm: bad act %d", act);
+  Epilogue ep{bias, residual, ldr, static_cast<__half*>(out_f16), ldo16, out_f32, ldo32, act};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (impl == CFFM_GEMM_CHECK) {
+    dim3 grid((N + CK_T - 1) / CK_T, (M + CK_T - 1) / CK_T);
+    gemm_check_kernel<<<grid, 256, 0, st>>>(static_cast<const __half*>(A), lda, static_cast<const __half*>(W), ldw, ep,
+                                            M, N, K);
+    return launch_status("gemm_check_kernel");
+  }
+  CFFM_REQUIRE(impl == CFFM_GEMM_TCGEN05, CFFM_E_BADARG, "gemm: bad impl %d", impl);
+  if (N % 128 == 0 || (N % 64 != 0 && N > 64)) return launch_tcgen05<128>(A, lda, W, ldw, ep, M, N, K, st);
+  return launch_tcgen05<64>(A, lda, W, ldw, ep, M, N, K, st);
+}

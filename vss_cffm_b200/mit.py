@@ -1,0 +1,258 @@
+"""MixVisionTransformer (SegFormer MiT-B0..B5) backbone, B200-native.
+
+Mirrors the reference plugin surface (mmseg/models/backbones/mix_transformer.py:203-423): classes
+registered in BACKBONES as ``mit_b0`` .. ``mit_b5``, ``**kwargs`` swallowed (configs pass
+``style='pytorch'``), ``init_weights(pretrained)``, ``forward(x) -> list of 4 NCHW maps`` at strides
+4/8/16/32, and the SAME state-dict keys and shapes, so reference checkpoints load unchanged.
+
+The nn.Module tree below only HOLDS parameters.  The arithmetic is a fixed sequence of C-ABI
+calls (``ops``) on fp16 token-major ("NHWC") activations with an fp32 residual stream:
+
+  patch embed  : im2col -> tcgen05 GEMM(+bias) -> LayerNorm(eps 1e-5)        (:173-200)
+  attention    : LN -> q GEMM ; [sr: im2col -> GEMM -> LN(1e-5)] -> kv GEMM ;
+                 fused softmax(q k^T d^-1/2) v with the <=225 keys in smem ;
+                 proj GEMM + residual (in place)                              (:96-117,:154)
+  Mix-FFN      : LN -> fc1 GEMM -> depthwise 3x3 + GELU -> fc2 GEMM + residual (:48-55,:155)
+  stage output : LN(eps 1e-6) -> fp16 NHWC (also the next stage's im2col input) (:321-349)
+"""
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from . import _abi, ops
+from .registry import BACKBONES
+from .workspace import Workspace
+
+_H, _F = torch.float16, torch.float32
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class _DWConv(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.dwconv = nn.Conv2d(dim, dim, 3, 1, 1, bias=True, groups=dim)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.dwconv = _DWConv(hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, num_heads, qkv_bias, sr_ratio):
+        super().__init__()
+        assert dim % num_heads == 0, f"dim {dim} should be divided by num_heads {num_heads}."
+        self.dim, self.num_heads, self.sr_ratio = dim, num_heads, sr_ratio
+        self.q = nn.Linear(dim, dim, bias=qkv_bias)
+        self.kv = nn.Linear(dim, dim * 2, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        if sr_ratio > 1:
+            self.sr = nn.Conv2d(dim, dim, kernel_size=sr_ratio, stride=sr_ratio)
+            self.norm = nn.LayerNorm(dim)                       # bare LayerNorm: eps 1e-5 (:77)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, num_heads, mlp_ratio, qkv_bias, norm_layer, sr_ratio):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = _Attention(dim, num_heads, qkv_bias, sr_ratio)
+        self.norm2 = norm_layer(dim)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+
+
+class _OverlapPatchEmbed(nn.Module):
+    def __init__(self, patch_size, stride, in_chans, embed_dim):
+        super().__init__()
+        self.patch_size, self.stride = patch_size, stride
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=stride, padding=patch_size // 2)
+        self.norm = nn.LayerNorm(embed_dim)                     # eps 1e-5 (:175)
+
+
+class MixVisionTransformer(nn.Module):
+    def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dims=(64, 128, 256, 512),
+                 num_heads=(1, 2, 4, 8), mlp_ratios=(4, 4, 4, 4), qkv_bias=False, qk_scale=None, drop_rate=0.,
+                 attn_drop_rate=0., drop_path_rate=0., norm_layer=nn.LayerNorm, depths=(3, 4, 6, 3),
+                 sr_ratios=(8, 4, 2, 1)):
+        super().__init__()
+        assert qk_scale is None, "qk_scale is never set by the reference's mit_b* (mix_transformer.py:373-423)"
+        self.num_classes = num_classes
+        self.depths = list(depths)
+        self.embed_dims, self.num_heads, self.sr_ratios = list(embed_dims), list(num_heads), list(sr_ratios)
+        self.in_chans = in_chans
+        chans = [in_chans] + list(embed_dims)
+        for s in range(4):
+            k, st = (7, 4) if s == 0 else (3, 2)
+            setattr(self, f"patch_embed{s + 1}", _OverlapPatchEmbed(k, st, chans[s], chans[s + 1]))
+            setattr(self, f"block{s + 1}", nn.ModuleList([
+                _Block(embed_dims[s], num_heads[s], mlp_ratios[s], qkv_bias, norm_layer, sr_ratios[s])
+                for _ in range(depths[s])]))
+            setattr(self, f"norm{s + 1}", norm_layer(embed_dims[s]))
+        self.apply(self._init_weights)
+        self._plan = None
+        self._ws = Workspace()
+        self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_plan())
+
+    # ------------------------------------------------------------------ reference-compatible API
+    @staticmethod
+    def _init_weights(m):
+        """mix_transformer.py:258-272."""
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+        elif isinstance(m, nn.Conv2d):
+            fan_out = m.kernel_size[0] * m.kernel_size[1] * m.out_channels // m.groups
+            m.weight.data.normal_(0, math.sqrt(2.0 / fan_out))
+            if m.bias is not None:
+                m.bias.data.zero_()
+
+    def init_weights(self, pretrained=None):
+        """mix_transformer.py:276-279: ``load_checkpoint(strict=False)`` when a path is given."""
+        if isinstance(pretrained, str):
+            ckpt = torch.load(pretrained, map_location="cpu")
+            sd = ckpt.get("state_dict", ckpt)
+            self.load_state_dict({k[9:] if k.startswith("backbone.") else k: v for k, v in sd.items()}, strict=False)
+
+    def invalidate_plan(self):
+        self._plan = None
+
+    def _apply(self, fn, *a, **k):
+        self._plan = None
+        return super()._apply(fn, *a, **k)
+
+    def train(self, mode=True):
+        if mode:
+            raise _abi.CffmError("vss_cffm_b200 implements the inference hot path only (eval mode); "
+                                 "training is out of scope (SURVEY.md section 8)")
+        return super().train(False)
+
+    # ------------------------------------------------------------------ plan: fp16 operand copies
+    def _build_plan(self):
+        dev = self.norm1.weight.device
+        if dev.type != "cuda":
+            raise _abi.CffmError("the backbone runs on a CUDA (sm_100) device only; call .cuda() first")
+        _abi.require_device()
+        h = lambda t: t.detach().to(dev, _H).contiguous()
+        f = lambda t: t.detach().to(dev, _F).contiguous()
+        stages = []
+        for s in range(4):
+            pe = getattr(self, f"patch_embed{s + 1}")
+            w = pe.proj.weight.detach()                          # (Cout, Cin, k, k) -> (Cout, k, k, Cin)
+            cout, cin, k, _ = w.shape
+            kdim = k * k * cin
+            kpad = _round_up(kdim, 8)
+            wp = torch.zeros(cout, kpad, device=dev, dtype=_H)
+            wp[:, :kdim] = w.permute(0, 2, 3, 1).reshape(cout, kdim).to(dev, _H)
+            st = dict(k=k, stride=pe.stride, pad=k // 2, cin=cin, cout=cout, kpad=kpad, w=wp, b=f(pe.proj.bias),
+                      ng=f(pe.norm.weight), nb=f(pe.norm.bias), eps=pe.norm.eps, blocks=[])
+            for blk in getattr(self, f"block{s + 1}"):
+                a, m = blk.attn, blk.mlp
+                b = dict(n1g=f(blk.norm1.weight), n1b=f(blk.norm1.bias), n1eps=blk.norm1.eps,
+                         n2g=f(blk.norm2.weight), n2b=f(blk.norm2.bias), n2eps=blk.norm2.eps,
+                         qw=h(a.q.weight), qb=f(a.q.bias) if a.q.bias is not None else None,
+                         kvw=h(a.kv.weight), kvb=f(a.kv.bias) if a.kv.bias is not None else None,
+                         pw=h(a.proj.weight), pb=f(a.proj.bias), sr=a.sr_ratio,
+                         f1w=h(m.fc1.weight), f1b=f(m.fc1.bias), f2w=h(m.fc2.weight), f2b=f(m.fc2.bias),
+                         dww=h(m.dwconv.dwconv.weight.detach().reshape(-1, 9).t()), dwb=f(m.dwconv.dwconv.bias))
+                if a.sr_ratio > 1:
+                    sw = a.sr.weight.detach()                    # (C, C, sr, sr) -> (C, sr, sr, C)
+                    b.update(srw=h(sw.permute(0, 2, 3, 1).reshape(sw.shape[0], -1)), srb=f(a.sr.bias),
+                             sng=f(a.norm.weight), snb=f(a.norm.bias), seps=a.norm.eps)
+                st["blocks"].append(b)
+            fn = getattr(self, f"norm{s + 1}")
+            st.update(fg=f(fn.weight), fb=f(fn.bias), feps=fn.eps)
+            stages.append(st)
+        self._plan = stages
+        return stages
+
+    # ------------------------------------------------------------------ forward
+    def forward_features(self, x):
+        """mix_transformer.py:313-349.  x (N,3,H,W) fp32 -> 4 fp16 NHWC maps returned as NCHW views."""
+        if x.dim() != 4 or x.shape[1] != self.in_chans:
+            raise _abi.CffmError(f"expected (N,{self.in_chans},H,W) input, got {tuple(x.shape)}")
+        plan = self._plan or self._build_plan()
+        dev = plan[0]["w"].device
+        x = x.to(dev, _F).contiguous()
+        ws = self._ws
+        N, _, H, W = x.shape
+        outs = []
+        cur, layout = x, 0
+        for s, st in enumerate(plan):
+            k, stride, pad, C = st["k"], st["stride"], st["pad"], st["cout"]
+            Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+            M = N * Ho * Wo
+            col = ws.get(f"s{s}.col", (M, st["kpad"]), _H)
+            ops.im2col(cur, layout, N, H, W, st["cin"], k, stride, pad, col)
+            pe32 = ws.get(f"s{s}.pe32", (M, C), _F)
+            ops.gemm(col, st["w"], bias=st["b"], out32=pe32)
+            xres = ws.get(f"s{s}.x", (M, C), _F)                 # fp32 residual stream
+            ops.layernorm(pe32, st["ng"], st["nb"], st["eps"], out32=xres)
+            xn = ws.get(f"s{s}.xn", (M, C), _H)
+            heads = self.num_heads[s]
+            d = C // heads
+            for b in st["blocks"]:
+                # ---- efficient self-attention
+                ops.layernorm(xres, b["n1g"], b["n1b"], b["n1eps"], out16=xn)
+                q = ws.get(f"s{s}.q", (M, C), _H)
+                ops.gemm(xn, b["qw"], bias=b["qb"], out16=q)
+                sr = b["sr"]
+                if sr > 1:
+                    Hs, Ws_ = (Ho - sr) // sr + 1, (Wo - sr) // sr + 1
+                    Ms = N * Hs * Ws_
+                    scol = ws.get(f"s{s}.srcol", (Ms, sr * sr * C), _H)
+                    ops.im2col(xn, 1, N, Ho, Wo, C, sr, sr, 0, scol)
+                    s32 = ws.get(f"s{s}.sr32", (Ms, C), _F)
+                    ops.gemm(scol, b["srw"], bias=b["srb"], out32=s32)
+                    kvin = ws.get(f"s{s}.srn", (Ms, C), _H)
+                    ops.layernorm(s32, b["sng"], b["snb"], b["seps"], out16=kvin)
+                    nkv = Hs * Ws_
+                else:
+                    kvin, Ms, nkv = xn, M, Ho * Wo
+                kv = ws.get(f"s{s}.kv", (Ms, 2 * C), _H)
+                ops.gemm(kvin, b["kvw"], bias=b["kvb"], out16=kv)
+                ao = ws.get(f"s{s}.ao", (M, C), _H)
+                ops.mha(q, kv[:, :C], kv[:, C:], ao, N, Ho * Wo, nkv, heads, d, d ** -0.5)
+                ops.gemm(ao, b["pw"], bias=b["pb"], residual=xres, out32=xres)
+                # ---- Mix-FFN
+                ops.layernorm(xres, b["n2g"], b["n2b"], b["n2eps"], out16=xn)
+                Ch = b["f1w"].shape[0]
+                h1 = ws.get(f"s{s}.h1", (M, Ch), _H)
+                ops.gemm(xn, b["f1w"], bias=b["f1b"], out16=h1)
+                h2 = ws.get(f"s{s}.h2", (M, Ch), _H)
+                ops.dwconv3x3_gelu(h1, b["dww"], b["dwb"], h2, N, Ho, Wo, Ch)
+                ops.gemm(h2, b["f2w"], bias=b["f2b"], residual=xres, out32=xres)
+            out = ws.get(f"s{s}.out", (M, C), _H)
+            ops.layernorm(xres, st["fg"], st["fb"], st["feps"], out16=out)
+            outs.append(out.view(N, Ho, Wo, C).permute(0, 3, 1, 2))   # logical NCHW, channels-last memory
+            cur, layout, H, W = out, 1, Ho, Wo
+        return outs
+
+    def forward(self, x):
+        return self.forward_features(x)
+
+
+def _variant(embed_dims, depths):
+    def ctor(self, **kwargs):                                    # kwargs (style='pytorch') are swallowed (:384-388)
+        MixVisionTransformer.__init__(
+            self, patch_size=4, embed_dims=embed_dims, num_heads=[1, 2, 5, 8], mlp_ratios=[4, 4, 4, 4],
+            qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), depths=depths, sr_ratios=[8, 4, 2, 1],
+            drop_rate=0.0, drop_path_rate=0.1)
+    return ctor
+
+
+for _name, _dims, _depths in (("mit_b0", [32, 64, 160, 256], [2, 2, 2, 2]), ("mit_b1", [64, 128, 320, 512], [2, 2, 2, 2]),
+                              ("mit_b2", [64, 128, 320, 512], [3, 4, 6, 3]), ("mit_b3", [64, 128, 320, 512], [3, 4, 18, 3]),
+                              ("mit_b4", [64, 128, 320, 512], [3, 8, 27, 3]), ("mit_b5", [64, 128, 320, 512], [3, 6, 40, 3])):
+    _cls = type(_name, (MixVisionTransformer,), {"__init__": _variant(_dims, _depths), "__module__": __name__})
+    globals()[_name] = BACKBONES.register_module()(_cls)

@@ -1,0 +1,197 @@
+"""Tensor-level wrappers over the C ABI (include/cffm_b200.h).
+
+PyTorch is used for device memory and the current stream only; every function below hands raw
+device pointers to libcffm_b200.so.  Each wrapper validates dtype / device / contiguity on the
+host so that a bad call fails here, with a Python traceback, instead of inside a kernel.
+"""
+import torch
+
+from . import _abi
+from ._abi import ACT_GELU, ACT_NONE, ACT_RELU, GEMM_CHECK, GEMM_TCGEN05  # noqa: F401
+
+_H, _F = torch.float16, torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name, rows2d=True):
+    if not t.is_cuda:
+        raise _abi.CffmError(f"{name}: expected a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise _abi.CffmError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise _abi.CffmError(f"{name}: innermost dimension must be contiguous")
+
+
+def _ld(t):
+    """Row stride (elements) of a 2-D row-major view; rows may be strided (column slices)."""
+    assert t.dim() == 2
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def gemm(a, w, bias=None, residual=None, out16=None, out32=None, act=ACT_NONE, impl=GEMM_TCGEN05):
+    """out = act(a @ w.T + bias) (+ residual).  a [M,K] fp16, w [N,K] fp16, bias fp32 [N],
+    residual fp32 [M,N] (may alias out32).  out16 / out32 are preallocated [M,N] views."""
+    _chk(a, _H, "gemm.a"); _chk(w, _H, "gemm.w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, (a.shape, w.shape)
+    for t, d, n in ((bias, _F, "bias"), (residual, _F, "residual"), (out16, _H, "out16"), (out32, _F, "out32")):
+        if t is not None:
+            _chk(t, d, "gemm." + n)
+    if bias is not None:
+        assert bias.numel() == N
+    for t in (residual, out16, out32):
+        if t is not None:
+            assert tuple(t.shape) == (M, N), (tuple(t.shape), M, N)
+    _abi.call("cffm_gemm_f16", _ptr(a), _ld(a), _ptr(w), _ld(w), _ptr(bias), _ptr(residual),
+              _ld(residual) if residual is not None else 0, _ptr(out16), _ld(out16) if out16 is not None else 0,
+              _ptr(out32), _ld(out32) if out32 is not None else 0, M, N, K, act, impl, _stream())
+
+
+def layernorm(x, gamma, beta, eps, out16=None, out32=None):
+    """Row LayerNorm of x [M,C] (fp32 or fp16)."""
+    assert x.dim() == 2 and x.dtype in (_H, _F)
+    _chk(x, x.dtype, "layernorm.x"); _chk(gamma, _F, "layernorm.gamma"); _chk(beta, _F, "layernorm.beta")
+    M, C = x.shape
+    if out16 is not None:
+        _chk(out16, _H, "layernorm.out16"); assert tuple(out16.shape) == (M, C)
+    if out32 is not None:
+        _chk(out32, _F, "layernorm.out32"); assert tuple(out32.shape) == (M, C)
+    _abi.call("cffm_layernorm", _ptr(x), int(x.dtype == _F), _ld(x), _ptr(gamma), _ptr(beta), float(eps),
+              _ptr(out16), _ld(out16) if out16 is not None else 0, _ptr(out32),
+              _ld(out32) if out32 is not None else 0, M, C, _stream())
+
+
+def im2col(x, layout, N, H, W, C, k, stride, pad, out):
+    """out [N*Ho*Wo, Kpad] fp16 patches, K order (ky,kx,c).  layout 0: fp32 NCHW, 1: fp16 NHWC."""
+    _chk(x, _F if layout == 0 else _H, "im2col.x"); _chk(out, _H, "im2col.out")
+    assert x.is_contiguous() and out.is_contiguous()
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    assert out.shape[0] == N * Ho * Wo, (out.shape, N, Ho, Wo)
+    _abi.call("cffm_im2col", _ptr(x), layout, N, H, W, C, k, stride, pad, _ptr(out), out.shape[1], _stream())
+
+
+def mha(q, k, v, out, batch, Nq, Nkv, heads, head_dim, scale):
+    """softmax(scale q k^T) v.  q [batch*Nq, heads*d], k / v [batch*Nkv, ...] (column slices ok)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _chk(t, _H, "mha." + n)
+    assert q.shape[0] == batch * Nq and k.shape[0] == batch * Nkv and v.shape[0] == batch * Nkv
+    assert _ld(k) == _ld(v)
+    _abi.call("cffm_mha_f16", _ptr(q), _ld(q), _ptr(k), _ptr(v), _ld(k), _ptr(out), _ld(out), batch, Nq, Nkv, heads,
+              head_dim, float(scale), _stream())
+
+
+def dwconv3x3_gelu(x, w9c, bias, out, N, H, W, C):
+    _chk(x, _H, "dwconv.x"); _chk(w9c, _H, "dwconv.w"); _chk(bias, _F, "dwconv.bias"); _chk(out, _H, "dwconv.out")
+    assert x.is_contiguous() and out.is_contiguous() and x.numel() == N * H * W * C == out.numel()
+    assert tuple(w9c.shape) == (9, C)
+    _abi.call("cffm_dwconv3x3_gelu", _ptr(x), _ptr(w9c), _ptr(bias), _ptr(out), N, H, W, C, _stream())
+
+
+def head_fuse(p, sizes, N, C, t_perm, shift, c_full=None, half32=None, half16=None):
+    """p: 4 fp16 NHWC maps [N,Hi,Wi,C]; sizes: [(H1,W1),...]."""
+    for t in p:
+        _chk(t, _H, "head_fuse.p"); assert t.is_contiguous()
+    _chk(shift, _F, "head_fuse.shift")
+    (H1, W1), (H2, W2), (H3, W3), (H4, W4) = sizes
+    if c_full is not None:
+        _chk(c_full, _H, "head_fuse.c_full"); assert c_full.is_contiguous()
+    if half32 is not None:
+        _chk(half32, _F, "head_fuse.half32")
+    if half16 is not None:
+        _chk(half16, _H, "head_fuse.half16")
+    _abi.call("cffm_head_fuse", _ptr(p[0]), _ptr(p[1]), _ptr(p[2]), _ptr(p[3]), N, H1, W1, H2, W2, H3, W3, H4, W4, C,
+              t_perm, _ptr(shift), _ptr(c_full), _ptr(half32), _ld(half32) if half32 is not None else 0,
+              _ptr(half16), _ld(half16) if half16 is not None else 0, _stream())
+
+
+def cffa_norm(x, gamma, beta, eps, xn, xt_pad, B, T, H, W, Hp, Wp, C):
+    _chk(x, _F, "cffa_norm.x"); _chk(xn, _H, "cffa_norm.xn"); _chk(xt_pad, _H, "cffa_norm.xt_pad")
+    assert x.is_contiguous() and xn.is_contiguous() and xt_pad.is_contiguous()
+    assert x.numel() == B * T * H * W * C == xn.numel() and xt_pad.numel() == B * Hp * Wp * C
+    _abi.call("cffm_cffa_norm", _ptr(x), _ptr(gamma), _ptr(beta), float(eps), _ptr(xn), _ptr(xt_pad), B, T, H, W, Hp,
+              Wp, C, _stream())
+
+
+def cffa_pool(xn, B, T, H, W, C, pool_w, pool_b, pooled):
+    _chk(xn, _H, "cffa_pool.xn"); _chk(pool_w, _F, "cffa_pool.pool_w"); _chk(pool_b, _F, "cffa_pool.pool_b")
+    _chk(pooled, _H, "cffa_pool.pooled")
+    assert pool_w.numel() == 49 + 49 + 9 + 4 and pool_b.numel() == 4 and pooled.is_contiguous()
+    _abi.call("cffm_cffa_pool", _ptr(xn), B, T, H, W, C, _ptr(pool_w), _ptr(pool_b), _ptr(pooled), _stream())
+
+
+def cfm_attention(qkv_t, kv_pooled, bias, out, B, H, W, C, heads, scale):
+    _chk(qkv_t, _H, "cfm.qkv_t"); _chk(kv_pooled, _H, "cfm.kv_pooled"); _chk(bias, _F, "cfm.bias"); _chk(out, _H, "cfm.out")
+    assert qkv_t.is_contiguous() and kv_pooled.is_contiguous() and bias.is_contiguous() and out.is_contiguous()
+    assert tuple(bias.shape) == (heads, 64, 320)
+    _abi.call("cffm_cfm_attention", _ptr(qkv_t), _ptr(kv_pooled), _ptr(bias), _ptr(out), B, H, W, C, heads,
+              float(scale), _stream())
+
+
+def cfm_key_sources(Hp, Wp, device):
+    out = torch.empty((Hp // 7) * (Wp // 7), 289, 3, dtype=torch.int32, device=device)
+    _abi.call("cffm_cfm_key_sources", Hp, Wp, _ptr(out), _stream())
+    return out
+
+
+def resize_nhwc_to_nchw(x, ncls, out, B, h, w, Ho, Wo):
+    assert x.dtype in (_H, _F)
+    _chk(x, x.dtype, "resize.x"); _chk(out, _F, "resize.out")
+    assert out.is_contiguous() and out.numel() == B * ncls * Ho * Wo
+    _abi.call("cffm_resize_nhwc_to_nchw", _ptr(x), int(x.dtype == _F), x.stride(-2) if x.dim() > 1 else ncls, _ptr(out),
+              B, h, w, ncls, Ho, Wo, _stream())
+
+
+def resize_argmax(logits, labels, B, ncls, h, w, Ho, Wo):
+    _chk(logits, _F, "resize_argmax.logits")
+    assert logits.is_contiguous() and labels.dtype == torch.int64 and labels.is_cuda and labels.is_contiguous()
+    assert logits.numel() == B * ncls * h * w and labels.numel() == B * Ho * Wo
+    _abi.call("cffm_resize_argmax", _ptr(logits), _ptr(labels), B, ncls, h, w, Ho, Wo, _stream())
+
+
+def resize_nchw(x, out):
+    _chk(x, _F, "resize_nchw.x"); _chk(out, _F, "resize_nchw.out")
+    assert x.is_contiguous() and out.is_contiguous() and x.shape[:2] == out.shape[:2]
+    B, C, h, w = x.shape
+    _abi.call("cffm_resize_nchw", _ptr(x), _ptr(out), B, C, h, w, out.shape[2], out.shape[3], _stream())
+
+
+def softmax_nchw(x, out):
+    _chk(x, _F, "softmax_nchw.x"); _chk(out, _F, "softmax_nchw.out")
+    assert x.is_contiguous() and out.is_contiguous() and x.shape == out.shape
+    B, C, h, w = x.shape
+    _abi.call("cffm_softmax_nchw", _ptr(x), _ptr(out), B, C, h * w, _stream())
+
+
+class KernelTimer:
+    """CUDA-event timing of selected entry points on the launching stream (bench.py's live roofline
+    measurement).  ``with KernelTimer({"cffm_cfm_attention"}) as kt: step()`` then ``kt.ms()``."""
+
+    def __init__(self, names):
+        self.names = set(names)
+        self.events = {n: [] for n in self.names}
+
+    def _hook(self, name, phase):
+        if name in self.names:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream())
+            self.events[name].append(ev)
+
+    def __enter__(self):
+        _abi.launch_hook = self._hook
+        return self
+
+    def __exit__(self, *exc):
+        _abi.launch_hook = None
+
+    def ms(self):
+        """name -> list of per-launch durations (ms); synchronises."""
+        torch.cuda.synchronize()
+        return {n: [a.elapsed_time(b) for a, b in zip(ev[0::2], ev[1::2])] for n, ev in self.events.items()}

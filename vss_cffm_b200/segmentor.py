@@ -1,0 +1,185 @@
+"""``EncoderDecoder_clips`` -- the caller of the hot path, same surface as the reference
+(mmseg/models/segmentors/encoder_decoder.py:295-591 on base.py:14-303), inference only.
+
+``model(img=[[T x (B,3,H,W)]], img_metas=[[dict x B]], return_loss=False)`` -> list of B
+``np.ndarray (H,W) int64`` label maps.  Differences in HOW (not what) it computes:
+
+  * frames are stacked frame-major ((T,B,...) instead of (B,T,...), :556-560) so that the B target
+    frames are contiguous for the CFFM kernels; per-clip results are unchanged;
+  * when the head early-returns (eval and T != head.num_clips, cffm_head.py:127-129) only the last
+    frame influences the output, so only the last frame is pushed through the backbone;
+  * final bilinear resize + softmax + argmax (:373-377, :542, :564) is one kernel (softmax is
+    monotone, so the argmax is taken on the interpolated logits).
+"""
+import torch
+import torch.nn as nn
+
+from . import _abi, ops
+from . import registry as builder
+from .registry import SEGMENTORS
+from .workspace import Workspace
+
+_F = torch.float32
+
+
+@SEGMENTORS.register_module()
+class EncoderDecoder_clips(nn.Module):
+    def __init__(self, backbone, decode_head, neck=None, auxiliary_head=None, train_cfg=None, test_cfg=None,
+                 pretrained=None):
+        super().__init__()
+        self.backbone = builder.build_backbone(backbone)
+        if neck is not None:
+            raise _abi.CffmError("necks are not used by any CFFM config and are out of scope")
+        if auxiliary_head is not None:
+            raise _abi.CffmError("auxiliary heads are training-only and out of scope")
+        self.decode_head = builder.build_head(decode_head)
+        self.align_corners = self.decode_head.align_corners
+        self.num_classes = self.decode_head.num_classes
+        if self.align_corners:
+            raise _abi.CffmError("align_corners=True is not used by any CFFM config and is not implemented")
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.fp16_enabled = False
+        self.init_weights(pretrained=pretrained)
+        assert self.with_decode_head
+        self._ws = Workspace()
+        for m in self.modules():
+            m.training = False
+
+    # ------------------------------------------------------------------ BaseSegmentor surface
+    @property
+    def with_neck(self):
+        return False
+
+    @property
+    def with_auxiliary_head(self):
+        return False
+
+    @property
+    def with_decode_head(self):
+        return hasattr(self, "decode_head") and self.decode_head is not None
+
+    def init_weights(self, pretrained=None):
+        self.backbone.init_weights(pretrained=pretrained)
+        self.decode_head.init_weights()
+
+    def train(self, mode=True):
+        if mode:
+            raise _abi.CffmError("vss_cffm_b200 implements the inference hot path only (eval mode); "
+                                 "training is out of scope (SURVEY.md section 8)")
+        return super().train(False)
+
+    def forward_train(self, *a, **k):
+        raise NotImplementedError("vss_cffm_b200 covers the inference hot path only (SURVEY.md section 8)")
+
+    def forward(self, img, img_metas, return_loss=True, **kwargs):
+        """base.py:135-149."""
+        if return_loss:
+            return self.forward_train(img, img_metas, **kwargs)
+        return self.forward_test(img, img_metas, **kwargs)
+
+    def forward_test(self, imgs, img_metas, **kwargs):
+        """base.py:76-111."""
+        for var, name in [(imgs, "imgs"), (img_metas, "img_metas")]:
+            if not isinstance(var, list):
+                raise TypeError(f"{name} must be a list, but got {type(var)}")
+        if len(imgs) != len(img_metas):
+            raise ValueError(f"num of augmentations ({len(imgs)}) != num of image meta ({len(img_metas)})")
+        for img_meta in img_metas:
+            for key in ("ori_shape", "img_shape", "pad_shape"):
+                shapes = [m[key] for m in img_meta]
+                assert all(s == shapes[0] for s in shapes)
+        if len(imgs) == 1:
+            return self.simple_test(imgs[0], img_metas[0], **kwargs)
+        return self.aug_test(imgs, img_metas, **kwargs)
+
+    def aug_test(self, imgs, img_metas, rescale=True):
+        raise NotImplementedError("aug_test cannot run in the reference either (wrong arity, "
+                                  "encoder_decoder.py:582 vs :518)")
+
+    # ------------------------------------------------------------------ the hot path
+    def extract_feat(self, img):
+        return self.backbone(img)
+
+    def _device(self):
+        return next(self.parameters()).device
+
+    def _stack(self, img):
+        """list of T (B,3,H,W) -> (frames (T,B,3,H,W) frame-major on the model's device, B, T)."""
+        if not isinstance(img, (list, tuple)):
+            if img.dim() != 5:
+                raise _abi.CffmError("expected a list of T (B,3,H,W) tensors or a (B,T,3,H,W) tensor")
+            img = list(img.unbind(1))                            # (B,T,3,H,W) as in forward_train
+        T, B = len(img), img[0].shape[0]
+        dev = self._device()
+        if dev.type != "cuda":
+            raise _abi.CffmError("the model runs on a CUDA (sm_100) device only; call .cuda() first (no CPU fallback)")
+        frames = self._ws.get("frames", (T, B) + tuple(img[0].shape[1:]), _F, device=dev)
+        for t, f in enumerate(img):                              # one (async, if pinned) copy per frame stack
+            frames[t].copy_(f, non_blocking=True)
+        return frames, B, T
+
+    def encode_decode_frames(self, frames, img_metas, B, T, **head_kw):
+        """Backbone + head on frame-major frames (T,B,3,H,W) -> (B, num_classes, H/4, W/4) logits."""
+        head = self.decode_head
+        if T != head.num_clips:                                  # early return: only the target frame matters
+            x = self.extract_feat(frames[-1])
+            return head.forward_test(x, img_metas, self.test_cfg, B, 1, frame_major=True, **head_kw)
+        x = self.extract_feat(frames.reshape(T * B, *frames.shape[2:]))
+        return head.forward_test(x, img_metas, self.test_cfg, B, T, frame_major=True, **head_kw)
+
+    def encode_decode(self, img, img_metas, batch_size, num_clips):
+        """Reference signature (:367-378): img (B*T,3,H,W) clip-major -> logits resized to (H,W)."""
+        H, W = img.shape[2:]
+        frames = img.reshape(batch_size, num_clips, *img.shape[1:]).transpose(0, 1).contiguous()
+        out = self.encode_decode_frames(frames.to(self._device(), _F), img_metas, batch_size, num_clips)
+        full = torch.empty(batch_size, self.num_classes, H, W, dtype=_F, device=out.device)
+        ops.resize_nchw(out, full)
+        return full
+
+    def whole_inference(self, img, img_meta, rescale, batch_size, num_clips):
+        seg_logit = self.encode_decode(img, img_meta, batch_size, num_clips)
+        ori = tuple(img_meta[0]["ori_shape"][:2])
+        if rescale and ori != tuple(seg_logit.shape[2:]):
+            out = torch.empty(*seg_logit.shape[:2], *ori, dtype=_F, device=seg_logit.device)
+            ops.resize_nchw(seg_logit, out)
+            seg_logit = out
+        return seg_logit
+
+    def inference(self, img, img_meta, rescale, batch_size, num_clips):
+        """Reference signature (:518-552): softmax probabilities (B, num_classes, H, W)."""
+        assert self.test_cfg["mode"] in ["slide", "whole"]
+        if self.test_cfg["mode"] == "slide":
+            raise _abi.CffmError("slide inference is not used by any CFFM config (test_cfg.mode='whole')")
+        seg_logit = self.whole_inference(img, img_meta, rescale, batch_size, num_clips)
+        out = torch.empty_like(seg_logit)
+        ops.softmax_nchw(seg_logit, out)
+        return self._flip(out, img_meta)
+
+    @staticmethod
+    def _flip(t, img_meta):
+        if img_meta[0].get("flip", False):
+            d = img_meta[0]["flip_direction"]
+            assert d in ["horizontal", "vertical"]
+            t = t.flip(dims=(-1,) if d == "horizontal" else (-2,))
+        return t
+
+    def predict_labels(self, img, img_meta, rescale=True, **head_kw):
+        """Device-side part of simple_test: int64 label maps (B,H,W) on the GPU."""
+        frames, B, T = self._stack(img)
+        H, W = frames.shape[-2:]
+        ori = tuple(img_meta[0]["ori_shape"][:2])
+        assert all(tuple(m["ori_shape"][:2]) == ori for m in img_meta)
+        logits = self.encode_decode_frames(frames, img_meta, B, T, **head_kw)     # (B,ncls,h,w)
+        h, w = logits.shape[2:]
+        if rescale and ori != (H, W):                            # two chained resizes (:373-377 then :507-514)
+            mid = torch.empty(B, self.num_classes, H, W, dtype=_F, device=logits.device)
+            ops.resize_nchw(logits, mid)
+            logits, h, w, H, W = mid, H, W, ori[0], ori[1]
+        labels = torch.empty(B, H, W, dtype=torch.int64, device=logits.device)
+        ops.resize_argmax(logits, labels, B, self.num_classes, h, w, H, W)
+        return self._flip(labels, img_meta)
+
+    def simple_test(self, img, img_meta, rescale=True, **head_kw):
+        """encoder_decoder.py:554-572: list of B (H,W) int64 numpy label maps."""
+        labels = self.predict_labels(img, img_meta, rescale, **head_kw)
+        return list(labels.cpu().numpy())
