@@ -11,7 +11,8 @@ EncoderDecoder_clips inference pass over one batch: frames -> int64 label maps.
   value : clip-frames/s (B*T*N / max-over-ranks device time), inputs resident in HBM, labels left in HBM
   e2e   : same metric through the public API with HOST (pinned) frames: H2D copy, forward, D2H of labels
           inside the timed region
-  roofline     : the CFM attention kernel (the kernel the metric names), timed live with CUDA events
+  roofline     : the dominant kernel family (tcgen05 GEMM) and, separately, the CFM attention kernel the metric
+                 names, both timed live with CUDA events around each launch
   cpu_baseline : the CPU oracle (a port of the reference's PyTorch path) on this box's host cores, bounded sample
 
 N>1: clips shard across ranks (the reference's own data-parallel strategy): weak
@@ -48,6 +49,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shard", default="clips", choices=["clips", "frames"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -187,15 +189,26 @@ def main():
     labels_host = torch.empty(B, H, W, dtype=torch.int64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
+    graphed = None
     if args.shard == "frames" and world > 1:
         from vss_cffm_b200 import parallel
         runner = parallel.FrameShardedRunner(model, world, rank)
         step_dev = lambda: runner.predict_labels(imgs_dev, metas)
+        step_eager = step_dev
     else:
-        step_dev = lambda: model.predict_labels(imgs_dev, metas)
+        step_eager = lambda: model.predict_labels(imgs_dev, metas)
+        if args.no_graph:
+            step_dev = step_eager
+        else:
+            graphed = model.make_graphed(B, T, H, W, metas)      # one cudaGraphLaunch per step
+            graphed.load(imgs_dev)
+            step_dev = graphed.replay
 
     def step_e2e():
-        lab = model.predict_labels(imgs_host, metas)          # H2D of the pinned frames happens inside
+        if graphed is not None:
+            lab = graphed(imgs_host)                              # H2D of the pinned frames + graph replay
+        else:
+            lab = model.predict_labels(imgs_host, metas)
         labels_host.copy_(lab, non_blocking=True)
         return lab
 
@@ -220,18 +233,22 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     n0 = _abi.n_launches
-    with ops.KernelTimer({"cffm_cfm_attention"}) as kt:
-        total_ms = timed(step_dev, args.steps)
+    total_ms = timed(step_dev, args.steps)
     launches = _abi.n_launches - n0
     barrier()
     clocks = sampler.stop() if sampler else None
-    cfm_ms = kt.ms()["cffm_cfm_attention"]
 
     for _ in range(3):
         step_e2e()
     barrier()
     e2e_ms = timed(step_e2e, args.steps)
     barrier()
+
+    # per-kernel CUDA-event timing of the same step, launched eagerly (events cannot bracket nodes of a graph)
+    ksteps = min(args.steps, 5)
+    with ops.KernelTimer({"cffm_gemm_f16", "cffm_cfm_attention"}) as kt:
+        eager_ms = timed(step_eager, ksteps)
+    krec = kt.results()
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -243,19 +260,48 @@ def main():
 
     if rank == 0:
         pk = peaks()
+        # ---- dominant kernel family: the tcgen05 GEMM (every Linear / conv of the path).  Algorithmic bytes of a
+        # launch = A + W + bias + residual + outputs, each once; FLOPs = 2 M N K.
+        gem = {}
+        g_bytes = g_flops = g_ms = 0.0
+        for name, a, ms in krec:
+            if name != "cffm_gemm_f16":
+                continue
+            Mg, Ng, Kg = a[11], a[12], a[13]
+            by = 2 * Mg * Kg + 2 * Ng * Kg + (4 * Ng if a[4] else 0) + (4 * Mg * Ng if a[5] else 0) + \
+                (2 * Mg * Ng if a[7] else 0) + (4 * Mg * Ng if a[9] else 0)
+            fl = 2 * Mg * Ng * Kg
+            g_bytes += by; g_flops += fl; g_ms += ms
+            e = gem.setdefault((Mg, Ng, Kg), [0, 0.0, by, fl])
+            e[0] += 1; e[1] += ms
+        n_gemm = sum(e[0] for e in gem.values())
+        top = sorted(gem.items(), key=lambda kv: -kv[1][1])[:5]
+        gbs = g_bytes / (g_ms * 1e-3) / 1e9 if g_ms else 0.0
+        roofline = {"kernel": "gemm_tcgen05_kernel (all launches of the step)", "bound": "hbm", "achieved": round(gbs, 1),
+                    "peak": pk["hbm"], "unit": "GB/s", "frac": round(gbs / pk["hbm"], 4), "traffic": None,
+                    "tensor_tflops": round(g_flops / (g_ms * 1e-3) / 1e12, 2) if g_ms else 0.0,
+                    "launches_per_step": n_gemm // ksteps, "ms_per_step": round(g_ms / ksteps, 4),
+                    "share_of_eager_step": round(g_ms / eager_ms, 4), "peak_source": pk["src"],
+                    "algorithmic_bytes_per_step": int(g_bytes / ksteps), "algorithmic_flops_per_step": int(g_flops / ksteps),
+                    "top_shapes": [{"M": k[0], "N": k[1], "K": k[2], "launches_per_step": v[0] // ksteps,
+                                    "avg_us": round(1e3 * v[1] / v[0], 2), "GBps": round(v[2] / (v[1] / v[0] * 1e-3) / 1e9, 1),
+                                    "frac": round(v[2] / (v[1] / v[0] * 1e-3) / 1e9 / pk["hbm"], 4)} for k, v in top],
+                    "note": "K <= 256 for nearly every GEMM of the path (AI 30-120 FLOP/B < ridge 210): HBM is the roof. "
+                            "Timed live with CUDA events around each launch of an eagerly launched step."}
+        cfm_ms = [ms for name, a, ms in krec if name == "cffm_cfm_attention"]
         cfm_avg_ms = sum(cfm_ms) / max(len(cfm_ms), 1)
         alg_bytes = CFM_BYTES_PER_CLIP_BLOCK * B                              # one launch = B clips of one block
         alg_flops = CFM_FLOPS_PER_CLIP_BLOCK * B
-        gbs = alg_bytes / (cfm_avg_ms * 1e-3) / 1e9
-        tfs = alg_flops / (cfm_avg_ms * 1e-3) / 1e12
-        roofline = {"kernel": "cfm_attention_kernel", "bound": "hbm", "achieved": round(gbs, 2), "peak": pk["hbm"],
-                    "unit": "GB/s", "frac": round(gbs / pk["hbm"], 5), "traffic": None,
-                    "tensor_tflops": round(tfs, 3), "tensor_frac_of_sustained": round(tfs / pk["tf_sust"], 5),
-                    "launch_ms": round(cfm_avg_ms, 5), "launches_timed": len(cfm_ms), "peak_source": pk["src"],
-                    "share_of_step": round(sum(cfm_ms) / total_ms, 4),
-                    "algorithmic": {"bytes_per_launch": alg_bytes, "flops_per_launch": alg_flops,
-                                    "note": "SURVEY.md 8(d): 9.6 MB and 1.1746 GFLOP per clip per block; un-fused attention "
-                                            "has AI 122 FLOP/B < ridge 210, so HBM is the binding roof"}}
+        cgbs = alg_bytes / (cfm_avg_ms * 1e-3) / 1e9
+        ctfs = alg_flops / (cfm_avg_ms * 1e-3) / 1e12
+        roofline_cfm = {"kernel": "cfm_attention_kernel", "bound": "hbm", "achieved": round(cgbs, 2), "peak": pk["hbm"],
+                        "unit": "GB/s", "frac": round(cgbs / pk["hbm"], 5), "traffic": None,
+                        "tensor_tflops": round(ctfs, 3), "tensor_frac_of_sustained": round(ctfs / pk["tf_sust"], 5),
+                        "launch_ms": round(cfm_avg_ms, 5), "launches_timed": len(cfm_ms),
+                        "share_of_eager_step": round(sum(cfm_ms) / eager_ms, 4),
+                        "algorithmic": {"bytes_per_launch": alg_bytes, "flops_per_launch": alg_flops,
+                                        "note": "SURVEY.md 8(d): 9.6 MB and 1.1746 GFLOP per clip per block; un-fused attention "
+                                                "has AI 122 FLOP/B < ridge 210, so HBM is the binding roof"}}
         out = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
@@ -268,7 +314,10 @@ def main():
                     "h2d_bytes_per_step": B * T * 3 * H * W * 4, "d2h_bytes_per_step": B * H * W * 8,
                     "api": "EncoderDecoder_clips.predict_labels(pinned host frames) + D2H of the int64 label maps"},
             "gpu_launches": launches,
+            "launch_mode": "eager" if graphed is None else f"CUDA graph replay ({graphed.kernels_per_replay} kernel nodes per step)",
+            "eager_ms_per_step": round(eager_ms / ksteps, 4),
             "roofline": roofline,
+            "roofline_cfm_attention": roofline_cfm,
         }
         if not args.no_cpu_baseline:
             v, ms, cores = cpu_reference_time(sd, 3, 1, clips=1)

@@ -148,6 +148,14 @@ int cffm_resize_nhwc_to_nchw(const void* in, int in_is_f32, int64_t ldc, float* 
 int cffm_resize_argmax(const float* logits, int64_t* labels, int B, int ncls, int h, int w, int Ho,
                        int Wo, void* stream);
 
+/* cffm_head.py:149 + encoder_decoder.py:373-377,542,564 in one pass: NHWC fp32 class scores
+ * [B,h,w,ldc] (first ncls channels) -> bilinear to (Hm,Wm) -> bilinear to (Ho,Wo) -> argmax ->
+ * int64 labels [B,Ho,Wo]; the two intermediate logit tensors are never written.  Requires the second
+ * stage to upsample by >= ~3.2x (else CFFM_E_UNSUPPORTED: use cffm_resize_nhwc_to_nchw +
+ * cffm_resize_argmax). */
+int cffm_upsample2_argmax(const float* scores, int64_t ldc, int64_t* labels, int B, int h, int w,
+                          int ncls, int Hm, int Wm, int Ho, int Wo, void* stream);
+
 /* Bilinear (align_corners=False) resize of fp32 NCHW maps [B,C,h,w] -> [B,C,Ho,Wo]: the extra
  * "rescale to ori_shape" step of whole_inference (encoder_decoder.py:507-514). */
 int cffm_resize_nchw(const float* in, float* out, int B, int C, int h, int w, int Ho, int Wo,

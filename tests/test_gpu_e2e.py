@@ -261,3 +261,17 @@ def test_rescale_to_ori_shape(full_model):
     assert torch.allclose(prob.sum(1), torch.ones_like(prob.sum(1)), atol=1e-4)
     agree = (prob.argmax(1).cpu().numpy()[0] == out[0]).mean()
     assert agree >= 0.999, agree
+
+
+def test_cuda_graph_replay_equals_eager(full_model):
+    """One captured pass replays bit-identically to the eager launch sequence, for new inputs too."""
+    m = full_model
+    metas = synth.img_metas(2, 480, 480)
+    runner = m.make_graphed(2, 4, 480, 480, metas)
+    assert runner.kernels_per_replay > 50
+    for seed in (7, 8):
+        imgs = synth.synth_clip(2, 4, 480, 480, seed=seed)
+        eager = m.predict_labels(imgs, metas).clone()
+        graphed = runner([t.pin_memory() for t in imgs]).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(eager, graphed)

@@ -347,3 +347,38 @@ def test_resize_nchw_softmax_argmax(ops, B, C, h, w, Ho, Wo):
     top2 = up.topk(2, dim=1).values
     margin = (top2[:, 0] - top2[:, 1])[labels.cpu() != ref]
     assert margin.numel() == 0 or margin.max().item() < 1e-5
+
+
+@pytest.mark.parametrize("B,h,w,Hm,Wm,Ho,Wo", [(2, 8, 12, 16, 24, 64, 96), (1, 60, 60, 120, 120, 480, 480),
+                                               (2, 16, 24, 16, 24, 64, 96), (1, 7, 9, 13, 18, 50, 70)])
+def test_upsample2_argmax_vs_two_resizes(ops, B, h, w, Hm, Wm, Ho, Wo):
+    """Fused (x2 resize, x4 resize, argmax) == resize -> resize -> softmax -> argmax (cffm_head.py:149,
+    encoder_decoder.py:373-377,542,564)."""
+    ncls, ldc = 124, 128
+    x = synth.synth_array((B, h, w, ldc), 33)
+    assert ops.upsample2_argmax_supported(Hm, Wm, Ho, Wo)
+    mid = F.interpolate(x[..., :ncls].permute(0, 3, 1, 2), size=(Hm, Wm), mode="bilinear", align_corners=False)
+    up = F.interpolate(mid, size=(Ho, Wo), mode="bilinear", align_corners=False)
+    ref = torch.softmax(up, 1).argmax(1)
+    labels = torch.empty(B, Ho, Wo, dtype=torch.int64, device="cuda")
+    ops.upsample2_argmax(x.view(-1, ldc).cuda(), ncls, labels, B, h, w, Hm, Wm, Ho, Wo)
+    got = labels.cpu()
+    agree = (got == ref).float().mean().item()
+    assert agree >= 0.9999, agree
+    top2 = up.topk(2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1])[got != ref]
+    assert margin.numel() == 0 or margin.max().item() < 1e-5          # only fp32 near-ties may flip
+    assert not ops.upsample2_argmax_supported(120, 120, 130, 130)       # weak upsampling: unfused path is used
+
+
+def test_gelu_epilogue_accuracy(ops):
+    """The one-MUFU erf of the GELU epilogue is exact to 3e-7 (tools/fit_erf.py): checked through a GEMM with
+    an identity weight over a dense sweep of pre-activations."""
+    M, K = 4096, 64
+    xs = torch.linspace(-9, 9, M * K).view(M, K)
+    a = h16(xs).cuda().half()
+    w = torch.eye(K, dtype=torch.float16, device="cuda")
+    out = torch.empty(M, K, dtype=torch.float32, device="cuda")
+    ops.gemm(a, w, out32=out, act=ops.ACT_GELU)
+    ref = F.gelu(a.double().cpu())
+    assert (out.cpu().double() - ref).abs().max().item() < 2e-6

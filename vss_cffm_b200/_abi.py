@@ -40,6 +40,7 @@ SIGNATURES = {
     "cffm_cfm_key_sources": ([i32, i32, vp, vp], i32),
     "cffm_resize_nhwc_to_nchw": ([vp, i32, i64, vp, i32, i32, i32, i32, i32, i32, vp], i32),
     "cffm_resize_argmax": ([vp, vp, i32, i32, i32, i32, i32, i32, vp], i32),
+    "cffm_upsample2_argmax": ([vp, i64, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
     "cffm_resize_nchw": ([vp, vp, i32, i32, i32, i32, i32, i32, vp], i32),
     "cffm_softmax_nchw": ([vp, vp, i32, i32, i64, vp], i32),
 }
@@ -89,7 +90,7 @@ def check(status, what):
     raise CffmError(f"{what}: {kind}: {msg}")
 
 
-launch_hook = None      # optional callable(name, phase) with phase 0 = before / 1 = after the launch (bench.py)
+launch_hook = None      # optional callable(name, phase, args): phase 0 = before / 1 = after the launch (bench.py)
 
 
 def call(name, *args):
@@ -97,12 +98,12 @@ def call(name, *args):
     global n_launches
     hook = launch_hook
     if hook is not None:
-        hook(name, 0)
+        hook(name, 0, args)
     st = getattr(load(), name)(*args)
     check(st, name)
     n_launches += 1
     if hook is not None:
-        hook(name, 1)
+        hook(name, 1, args)
 
 
 def require_device():

@@ -349,6 +349,16 @@ class CFFMHead_clips_resize1_8(BaseDecodeHead_clips_flow):
         inputs: 4 feature maps (N, C_i, H_i, W_i), N = batch_size*num_clips frames in the reference's
         clip-major order, or frame-major when ``frame_major=True`` (what EncoderDecoder_clips of this
         package feeds).  Returns (batch_size, num_classes, H_1, W_1) fp32 logits."""
+        lg, (hs, ws_), (h, w) = self.forward_scores(inputs, batch_size, num_clips, img_metas, centers=centers,
+                                                    frame_major=frame_major)
+        out = torch.empty(batch_size, self.num_classes, h, w, dtype=_F, device=lg.device)
+        ops.resize_nhwc_to_nchw(lg, self.num_classes, out, batch_size, hs, ws_, h, w)    # (:149); identity when early
+        return out
+
+    def forward_scores(self, inputs, batch_size, num_clips, img_metas=None, *, centers=None, frame_major=False):
+        """Everything of ``forward`` up to (not including) the last bilinear resize: class scores of the target
+        frames, NHWC fp32 ``[B*hs*ws, ncp]`` (first num_classes columns valid), their size (hs, ws) and the size
+        (h, w) the reference resizes them to.  EncoderDecoder_clips fuses that resize with its own."""
         assert batch_size is not None and num_clips is not None
         P = self._plan or self._build_plan()
         ws = self._ws
@@ -376,9 +386,7 @@ class CFFMHead_clips_resize1_8(BaseDecodeHead_clips_flow):
             ct = c_full[(T - 1) * B * h * w:]                    # frame-major: target frames are last
             lg = ws.get("lg_full", (B * h * w, ncp), _F)
             ops.gemm(ct, P["pred_w"], bias=P["pred_b"], out32=lg)
-            out = torch.empty(B, ncls, h, w, dtype=_F, device=lg.device)
-            ops.resize_nhwc_to_nchw(lg, ncls, out, B, h, w, h, w)
-            return out
+            return lg, (h, w), (h, w)
         if num_clips != 4:
             raise _abi.CffmError("CFFM needs exactly 3 reference frames + 1 target (focal_l_clips=[1,2,3], "
                                  f"cffm_head.py:93-94); got num_clips={num_clips}")
@@ -428,9 +436,7 @@ class CFFMHead_clips_resize1_8(BaseDecodeHead_clips_flow):
             if centers is None:
                 centers = self._load_centers(img_metas, batch_size, lg.device)
             self._cluster_branch(P, xt0, centers, lg, B, HW)
-        out = torch.empty(B, ncls, h, w, dtype=_F, device=lg.device)
-        ops.resize_nhwc_to_nchw(lg, ncls, out, B, h2, w2, h, w)          # (:149)
-        return out
+        return lg, (h2, w2), (h, w)
 
     def _cluster_branch(self, P, xt0, centers, lg, B, HW):
         """decoder_swin + linear_pred3, accumulated into ``lg`` with weight 0.5 (cffm_head.py:519-532;

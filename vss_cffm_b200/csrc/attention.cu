@@ -359,12 +359,14 @@ cfm_attention_kernel(const __half* __restrict__ qkv_t, const __half* __restrict_
   }
 }
 
-template <typename K>
-int set_smem_attr(K kernel, int bytes) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(%d bytes): %s", bytes, cudaGetErrorString(e));
-    return -(int)e;
+constexpr int SMEM_CAP = 200 * 1024;
+// Raises the dynamic shared-memory cap of `kernel` once per process (never inside a later stream capture).
+template <auto Kernel>                                          // one static per kernel, not per signature
+int set_smem_attr() {
+  static cudaError_t err = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP);
+  if (err != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(%d bytes): %s", SMEM_CAP, cudaGetErrorString(err));
+    return -(int)err;
   }
   return CFFM_OK;
 }
@@ -391,12 +393,12 @@ extern "C" int cffm_mha_f16(const void* q, int64_t ldq, const void* k, const voi
   const float sl = scale * 1.4426950408889634f;
   int rc;
   if (head_dim == 64) {
-    if ((rc = set_smem_attr(mha_small_kv_kernel<64>, smem))) return rc;
+    if ((rc = set_smem_attr<mha_small_kv_kernel<64>>())) return rc;
     mha_small_kv_kernel<64><<<grid, 256, smem, st>>>(static_cast<const __half*>(q), ldq, static_cast<const __half*>(k),
                                                      static_cast<const __half*>(v), ldkv, static_cast<__half*>(out),
                                                      ldo, Nq, Nkv, nkv_pad, sl);
   } else {
-    if ((rc = set_smem_attr(mha_small_kv_kernel<32>, smem))) return rc;
+    if ((rc = set_smem_attr<mha_small_kv_kernel<32>>())) return rc;
     mha_small_kv_kernel<32><<<grid, 256, smem, st>>>(static_cast<const __half*>(q), ldq, static_cast<const __half*>(k),
                                                      static_cast<const __half*>(v), ldkv, static_cast<__half*>(out),
                                                      ldo, Nq, Nkv, nkv_pad, sl);
@@ -417,7 +419,7 @@ extern "C" int cffm_cfm_attention(const void* qkv_t, const void* kv_pooled, cons
   const int nW = (Hp / WS) * (Wp / WS);
   CFFM_REQUIRE(B <= 65535, CFFM_E_UNSUPPORTED, "cfm_attention: B too large");
   const int smem = 2 * NKEYS_PAD * 40 * 2 + NKEYS_PAD * 4;
-  int rc = set_smem_attr(cfm_attention_kernel, smem);
+  int rc = set_smem_attr<cfm_attention_kernel>();
   if (rc) return rc;
   dim3 grid(nW, heads, B);
   cfm_attention_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(

@@ -23,45 +23,78 @@ __device__ __forceinline__ Lerp lerp_coord(int dst, float scale, int in_size) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, row kept in registers (C <= 512), two-pass fp32 statistics.
-template <bool IN_F32>
+// LayerNorm.  A row of C channels is C/4 four-element vectors handled by a group of L lanes (L = the
+// power of two >= C/4, capped at 32), NV vectors per lane kept in registers; 32/L rows per warp, two-pass
+// fp32 statistics with intra-group shuffles.  All global accesses are 16-byte (fp32) / 8-byte (fp16).
+template <bool IN_F32, int L, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ xin, int64_t ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ o16, int64_t ldo16,
                  float* __restrict__ o32, int64_t ldo32, int M, int C) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  constexpr int RPW = 32 / L;                                  // rows per warp
   const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  constexpr int MAXPL = 16;
-  float v[MAXPL];
-  float sum = 0.f;
+  const int gl = lane % L;                                     // lane inside the row group
+  const int nvec = C >> 2;
+  const float invC = 1.f / static_cast<float>(C);
+  float4 g[NV], b[NV];
 #pragma unroll
-  for (int i = 0; i < MAXPL; ++i) {
-    const int c = lane + 32 * i;
-    float x = 0.f;
-    if (c < C) {
-      if (IN_F32) x = static_cast<const float*>(xin)[static_cast<int64_t>(row) * ldx + c];
-      else x = __half2float(static_cast<const __half*>(xin)[static_cast<int64_t>(row) * ldx + c]);
+  for (int i = 0; i < NV; ++i) {
+    const int v = gl + i * L;
+    g[i] = v < nvec ? *reinterpret_cast<const float4*>(gamma + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    b[i] = v < nvec ? *reinterpret_cast<const float4*>(beta + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int64_t warp_global = (blockIdx.x * 256ll + threadIdx.x) >> 5;
+  const int64_t nwarps = (gridDim.x * 256ll) >> 5;
+  for (int64_t rb = warp_global * RPW; rb < M; rb += nwarps * RPW) {      // warp-uniform trip count (shuffles inside)
+    const int64_t row = rb + lane / L;
+    const bool rv = row < M;
+    float4 x[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = gl + i * L;
+      x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rv && v < nvec) {
+        if (IN_F32) {
+          x[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(xin) + row * ldx + 4 * v);
+        } else {
+          const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const __half*>(xin) + row * ldx + 4 * v);
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+          x[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+      }
+      sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
     }
-    v[i] = x;
-    sum += x;
-  }
-  const float mean = warp_sum(sum) / C;
-  float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXPL; ++i) {
-    const int c = lane + 32 * i;
-    const float d = c < C ? v[i] - mean : 0.f;
-    sq += d * d;
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / C + eps);
+    for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * invC;
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXPL; ++i) {
-    const int c = lane + 32 * i;
-    if (c < C) {
-      const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
-      if (o16) o16[static_cast<int64_t>(row) * ldo16 + c] = __float2half_rn(y);
-      if (o32) o32[static_cast<int64_t>(row) * ldo32 + c] = y;
+    for (int i = 0; i < NV; ++i) {
+      if (gl + i * L < nvec) {
+        x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
+        sq += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
+      }
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * invC + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = gl + i * L;
+      if (rv && v < nvec) {
+        float4 y;
+        y.x = x[i].x * rstd * g[i].x + b[i].x; y.y = x[i].y * rstd * g[i].y + b[i].y;
+        y.z = x[i].z * rstd * g[i].z + b[i].z; y.w = x[i].w * rstd * g[i].w + b[i].w;
+        if (o32) *reinterpret_cast<float4*>(o32 + row * ldo32 + 4 * v) = y;
+        if (o16) {
+          uint2 h;
+          h.x = pack_half2(y.x, y.y);
+          h.y = pack_half2(y.z, y.w);
+          *reinterpret_cast<uint2*>(o16 + row * ldo16 + 4 * v) = h;
+        }
+      }
     }
   }
 }
@@ -90,59 +123,104 @@ im2col_nhwc_kernel(const __half* __restrict__ x, int N, int H, int W, int C, int
   }
 }
 
+// fp32 NCHW image -> fp16 patches.  One CTA per output row (n, oy): the k input rows of every channel are
+// staged in shared memory with coalesced reads (fp32 -> fp16 once), then each thread assembles 16-byte
+// chunks of the patch matrix, so the (dominant) output traffic is written as full 16-byte stores.
 __global__ void __launch_bounds__(256)
 im2col_nchw_f32_kernel(const float* __restrict__ x, int N, int H, int W, int C, int k, int stride, int pad, int Ho,
                        int Wo, __half* __restrict__ A, int Kpad) {
-  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * Kpad;
-  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
-    const int kcol = static_cast<int>(i % Kpad);
-    const int64_t m = i / Kpad;
-    float val = 0.f;
-    if (kcol < k * k * C) {
-      const int tap = kcol / C, c = kcol % C;
-      const int ky = tap / k, kx = tap % k;
-      const int ox = static_cast<int>(m % Wo), oy = static_cast<int>((m / Wo) % Ho), n = static_cast<int>(m / (Wo * Ho));
-      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = x[((static_cast<int64_t>(n) * C + c) * H + iy) * W + ix];
+  extern __shared__ __align__(16) uint8_t im_smem[];
+  __half* rows = reinterpret_cast<__half*>(im_smem);           // [C][k][Wp], Wp = W + 2*pad (zero borders)
+  const int Wp = W + 2 * pad;
+  const int oy = blockIdx.x % Ho, n = blockIdx.x / Ho;
+  for (int i = threadIdx.x; i < C * k * Wp; i += 256) {
+    const int xx = i % Wp - pad, ky = (i / Wp) % k, c = i / (Wp * k);
+    const int iy = oy * stride - pad + ky;
+    float v = 0.f;
+    if (xx >= 0 && xx < W && iy >= 0 && iy < H) v = x[((static_cast<int64_t>(n) * C + c) * H + iy) * W + xx];
+    rows[i] = __float2half_rn(v);
+  }
+  __syncthreads();
+  const int chunks = Kpad / 8, kdim = k * k * C;
+  __half* Arow = A + (static_cast<int64_t>(n) * Ho + oy) * Wo * Kpad;
+  for (int i = threadIdx.x; i < Wo * chunks; i += 256) {
+    const int ch = i % chunks, ox = i / chunks;
+    __align__(16) __half v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int kc = ch * 8 + e;
+      __half h = __float2half_rn(0.f);
+      if (kc < kdim) {
+        const int c = kc % C, tap = kc / C, kx = tap % k, ky = tap / k;
+        h = rows[(c * k + ky) * Wp + ox * stride + kx];
+      }
+      v[e] = h;
     }
-    A[i] = __float2half_rn(val);
+    *reinterpret_cast<uint4*>(Arow + static_cast<int64_t>(ox) * Kpad + ch * 8) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 3x3 (pad 1) + bias + GELU, NHWC fp16, 8 channels per thread
+// depthwise 3x3 (pad 1) + bias + GELU, NHWC fp16.  One thread = 8 channels x a strip of 4 horizontally
+// adjacent pixels: each input row of the strip is loaded once (6 x 16 B) and re-used by the 3 horizontal
+// taps of 4 outputs (4.5 loads per output instead of 9); a warp reads 512 contiguous bytes per tap at C=256.
+constexpr int DW_PX = 4;
 __global__ void __launch_bounds__(256)
 dwconv3x3_gelu_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
                       __half* __restrict__ out, int N, int H, int W, int C) {
-  const int chunks = C / 8;
-  const int64_t total = static_cast<int64_t>(N) * H * W * chunks;
+  const int chunks = C / 8, strips = (W + DW_PX - 1) / DW_PX;
+  const int64_t total = static_cast<int64_t>(N) * H * strips * chunks;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
     const int c = static_cast<int>(i % chunks) * 8;
     const int64_t p = i / chunks;
-    const int xx = static_cast<int>(p % W), yy = static_cast<int>((p / W) % H), n = static_cast<int>(p / (W * H));
-    float acc[8];
+    const int x0 = static_cast<int>(p % strips) * DW_PX, yy = static_cast<int>((p / strips) % H);
+    const int n = static_cast<int>(p / (static_cast<int64_t>(strips) * H));
+    float acc[DW_PX][8];
     {
       const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
-      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+#pragma unroll
+      for (int q = 0; q < DW_PX; ++q) {
+        acc[q][0] = b0.x; acc[q][1] = b0.y; acc[q][2] = b0.z; acc[q][3] = b0.w;
+        acc[q][4] = b1.x; acc[q][5] = b1.y; acc[q][6] = b1.z; acc[q][7] = b1.w;
+      }
     }
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = yy + ky - 1;
       if (iy < 0 || iy >= H) continue;
+      const __half* row = x + (static_cast<int64_t>(n) * H + iy) * W * C + c;
+      half8 xv[DW_PX + 2];
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = xx + kx - 1;
-        if (ix < 0 || ix >= W) continue;
-        float xv[8], wv[8];
-        unpack8(*reinterpret_cast<const half8*>(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * C + c), xv);
-        unpack8(*reinterpret_cast<const half8*>(w + (ky * 3 + kx) * C + c), wv);
+      for (int j = 0; j < DW_PX + 2; ++j) {
+        const int ix = x0 + j - 1;
+        if (ix >= 0 && ix < W) xv[j] = *reinterpret_cast<const half8*>(row + static_cast<int64_t>(ix) * C);
+        else { xv[j].h[0] = xv[j].h[1] = xv[j].h[2] = xv[j].h[3] = __floats2half2_rn(0.f, 0.f); }
+      }
+      float wf[3][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(xv[e], wv[e], acc[e]);
+      for (int kx = 0; kx < 3; ++kx) unpack8(*reinterpret_cast<const half8*>(w + (ky * 3 + kx) * C + c), wf[kx]);
+#pragma unroll
+      for (int j = 0; j < DW_PX + 2; ++j) {
+        float xf[8];
+        unpack8(xv[j], xf);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int q = j - kx;                                 // output pixel that sees column j through tap kx
+          if (q >= 0 && q < DW_PX) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[q][e] = fmaf(xf[e], wf[kx][e], acc[q][e]);
+          }
+        }
       }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = gelu_erf(acc[e]);
-    *reinterpret_cast<half8*>(out + p * C + c) = pack8(acc);
+    for (int q = 0; q < DW_PX; ++q) {
+      if (x0 + q < W) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[q][e] = gelu_erf(acc[q][e]);
+        *reinterpret_cast<half8*>(out + ((static_cast<int64_t>(n) * H + yy) * W + x0 + q) * C + c) = pack8(acc[q]);
+      }
+    }
   }
 }
 
@@ -406,6 +484,49 @@ softmax_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int B
   }
 }
 
+// Two chained bilinear resizes + argmax in one pass: NHWC fp32 class scores [B,h,w,ldc] -> (Hm,Wm) ->
+// (Ho,Wo) -> labels.  cffm_head.py:149 followed by encoder_decoder.py:373-377,542,564 (softmax is
+// monotone).  One CTA = a 16x16 tile of output pixels: the (<= UP_MT x UP_MT) intermediate-resolution
+// values it needs are computed once per class into shared memory from the low-resolution map
+// (channel-contiguous = coalesced reads), then every thread scans the classes of its own pixel.
+constexpr int UP_TILE = 16, UP_MT = 8;
+__global__ void __launch_bounds__(256)
+upsample2_argmax_kernel(const float* __restrict__ lg, int64_t ldc, int64_t* __restrict__ labels, int h, int w,
+                        int ncls, int Hm, int Wm, int Ho, int Wo) {
+  extern __shared__ __align__(16) uint8_t up_smem[];
+  float* mid = reinterpret_cast<float*>(up_smem);              // [UP_MT*UP_MT][CP], CP odd -> conflict-free
+  const int CP = ncls | 1;
+  const int b = blockIdx.z, Y0 = blockIdx.y * UP_TILE, X0 = blockIdx.x * UP_TILE;
+  const float sy1 = static_cast<float>(h) / Hm, sx1 = static_cast<float>(w) / Wm;
+  const float sy2 = static_cast<float>(Hm) / Ho, sx2 = static_cast<float>(Wm) / Wo;
+  const int my0 = lerp_coord(Y0, sy2, Hm).i0, mx0 = lerp_coord(X0, sx2, Wm).i0;
+  const int my1 = lerp_coord(min(Y0 + UP_TILE, Ho) - 1, sy2, Hm).i1, mx1 = lerp_coord(min(X0 + UP_TILE, Wo) - 1, sx2, Wm).i1;
+  const int nmy = my1 - my0 + 1, nmx = mx1 - mx0 + 1;          // host guarantees <= UP_MT
+  const float* base = lg + static_cast<int64_t>(b) * h * w * ldc;
+  for (int i = threadIdx.x; i < nmy * nmx * ncls; i += 256) {
+    const int c = i % ncls, pos = i / ncls, mx = pos % nmx, my = pos / nmx;
+    const Lerp ly = lerp_coord(my0 + my, sy1, h), lx = lerp_coord(mx0 + mx, sx1, w);
+    const float v00 = base[(static_cast<int64_t>(ly.i0) * w + lx.i0) * ldc + c], v01 = base[(static_cast<int64_t>(ly.i0) * w + lx.i1) * ldc + c];
+    const float v10 = base[(static_cast<int64_t>(ly.i1) * w + lx.i0) * ldc + c], v11 = base[(static_cast<int64_t>(ly.i1) * w + lx.i1) * ldc + c];
+    mid[(my * UP_MT + mx) * CP + c] = ly.w0 * (lx.w0 * v00 + lx.w1 * v01) + ly.w1 * (lx.w0 * v10 + lx.w1 * v11);
+  }
+  __syncthreads();
+  const int Y = Y0 + threadIdx.x / UP_TILE, X = X0 + threadIdx.x % UP_TILE;
+  if (Y >= Ho || X >= Wo) return;
+  const Lerp ly = lerp_coord(Y, sy2, Hm), lx = lerp_coord(X, sx2, Wm);
+  const float* p00 = mid + ((ly.i0 - my0) * UP_MT + (lx.i0 - mx0)) * CP;
+  const float* p01 = mid + ((ly.i0 - my0) * UP_MT + (lx.i1 - mx0)) * CP;
+  const float* p10 = mid + ((ly.i1 - my0) * UP_MT + (lx.i0 - mx0)) * CP;
+  const float* p11 = mid + ((ly.i1 - my0) * UP_MT + (lx.i1 - mx0)) * CP;
+  float best = -INFINITY;
+  int arg = 0;
+  for (int c = 0; c < ncls; ++c) {
+    const float v = ly.w0 * (lx.w0 * p00[c] + lx.w1 * p01[c]) + ly.w1 * (lx.w0 * p10[c] + lx.w1 * p11[c]);
+    if (v > best) { best = v; arg = c; }
+  }
+  labels[(static_cast<int64_t>(b) * Ho + Y) * Wo + X] = arg;
+}
+
 inline int grid_for(int64_t work_items, int per_block = 256) {
   int64_t g = (work_items + per_block - 1) / per_block;
   const int64_t cap = 148 * 16;                               // grid-stride: a few waves over 148 SMs
@@ -417,20 +538,42 @@ inline int grid_for(int64_t work_items, int per_block = 256) {
 
 using namespace cffm;
 
+template <bool F32, int L, int NV>
+static void launch_ln(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, __half* o16,
+                      int64_t ldo16, float* o32, int64_t ldo32, int M, int C, cudaStream_t st) {
+  constexpr int RPW = 32 / L;
+  const int64_t warps = (static_cast<int64_t>(M) + RPW - 1) / RPW;
+  int64_t grid = (warps + 7) / 8;
+  const int64_t cap = 148 * 8 * 4;                             // 8 resident CTAs per SM, a few rows per warp
+  if (grid > cap) grid = cap;
+  layernorm_kernel<F32, L, NV><<<static_cast<int>(grid), 256, 0, st>>>(x, ldx, gamma, beta, eps, o16, ldo16, o32, ldo32, M, C);
+}
+
 extern "C" int cffm_layernorm(const void* x, int x_is_f32, int64_t ldx, const float* gamma, const float* beta,
                               float eps, void* out_f16, int64_t ldo16, float* out_f32, int64_t ldo32, int M, int C,
                               void* stream) {
   CFFM_REQUIRE(x && gamma && beta && (out_f16 || out_f32), CFFM_E_BADARG, "layernorm: null pointer");
   CFFM_REQUIRE(M > 0 && C > 0, CFFM_E_BADARG, "layernorm: non-positive size");
-  CFFM_REQUIRE(C <= 512, CFFM_E_UNSUPPORTED, "layernorm: C=%d > 512", C);
+  CFFM_REQUIRE(C <= 512 && C % 4 == 0, CFFM_E_UNSUPPORTED, "layernorm: need C %% 4 == 0 and C <= 512, got %d", C);
+  CFFM_REQUIRE(ldx % 4 == 0 && (!out_f16 || ldo16 % 4 == 0) && (!out_f32 || ldo32 % 4 == 0) && aligned16(gamma) &&
+                   aligned16(beta) && (reinterpret_cast<uintptr_t>(x) & (x_is_f32 ? 15 : 7)) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out_f16) & 7) == 0 && aligned16(out_f32),
+               CFFM_E_BADARG, "layernorm: misaligned pointer or stride");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = (M + 7) / 8;
-  if (x_is_f32)
-    layernorm_kernel<true><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, static_cast<__half*>(out_f16), ldo16,
-                                                 out_f32, ldo32, M, C);
-  else
-    layernorm_kernel<false><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, static_cast<__half*>(out_f16), ldo16,
-                                                  out_f32, ldo32, M, C);
+  __half* o16 = static_cast<__half*>(out_f16);
+  const int nvec = C / 4;
+#define CFFM_LN(L, NV)                                                                                       \
+  do {                                                                                                       \
+    if (x_is_f32) launch_ln<true, L, NV>(x, ldx, gamma, beta, eps, o16, ldo16, out_f32, ldo32, M, C, st);    \
+    else launch_ln<false, L, NV>(x, ldx, gamma, beta, eps, o16, ldo16, out_f32, ldo32, M, C, st);            \
+  } while (0)
+  if (nvec <= 8) CFFM_LN(8, 1);
+  else if (nvec <= 16) CFFM_LN(16, 1);
+  else if (nvec <= 32) CFFM_LN(32, 1);
+  else if (nvec <= 64) CFFM_LN(32, 2);
+  else if (nvec <= 96) CFFM_LN(32, 3);
+  else CFFM_LN(32, 4);
+#undef CFFM_LN
   return launch_status("layernorm_kernel");
 }
 
@@ -448,8 +591,13 @@ extern "C" int cffm_im2col(const void* x, int layout, int N, int H, int W, int C
         static_cast<const __half*>(x), N, H, W, C, k, stride, pad, Ho, Wo, static_cast<__half*>(A), Kpad);
   } else {
     CFFM_REQUIRE(layout == 0, CFFM_E_BADARG, "im2col: bad layout %d", layout);
-    im2col_nchw_f32_kernel<<<grid_for(static_cast<int64_t>(N) * Ho * Wo * Kpad), 256, 0, st>>>(
-        static_cast<const float*>(x), N, H, W, C, k, stride, pad, Ho, Wo, static_cast<__half*>(A), Kpad);
+    const int smem = C * k * (W + 2 * pad) * 2;
+    CFFM_REQUIRE(smem <= 200 * 1024 && aligned16(A), CFFM_E_UNSUPPORTED,
+                 "im2col: NCHW path stages C*k*(W+2*pad) halves (%d bytes) in shared memory", smem);
+    static cudaError_t e = cudaFuncSetAttribute(im2col_nchw_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    CFFM_REQUIRE(e == cudaSuccess, -(int)e, "im2col: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    im2col_nchw_f32_kernel<<<N * Ho, 256, smem, st>>>(static_cast<const float*>(x), N, H, W, C, k, stride, pad, Ho, Wo,
+                                                       static_cast<__half*>(A), Kpad);
   }
   return launch_status("im2col_kernel");
 }
@@ -459,7 +607,7 @@ extern "C" int cffm_dwconv3x3_gelu(const void* x, const void* w, const float* bi
   CFFM_REQUIRE(x && w && bias && out, CFFM_E_BADARG, "dwconv: null pointer");
   CFFM_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, CFFM_E_UNSUPPORTED, "dwconv: need C %% 8 == 0");
   CFFM_REQUIRE(aligned16(x) && aligned16(w) && aligned16(bias) && aligned16(out), CFFM_E_BADARG, "dwconv: misaligned");
-  dwconv3x3_gelu_kernel<<<grid_for(static_cast<int64_t>(N) * H * W * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  dwconv3x3_gelu_kernel<<<grid_for(static_cast<int64_t>(N) * H * ((W + DW_PX - 1) / DW_PX) * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), static_cast<const __half*>(w), bias, static_cast<__half*>(out), N, H, W, C);
   return launch_status("dwconv3x3_gelu_kernel");
 }
@@ -539,4 +687,23 @@ extern "C" int cffm_softmax_nchw(const float* in, float* out, int B, int C, int6
   CFFM_REQUIRE(B > 0 && C > 0 && HW > 0, CFFM_E_BADARG, "softmax_nchw: bad size");
   softmax_nchw_kernel<<<grid_for(static_cast<int64_t>(B) * HW), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, B, C, HW);
   return launch_status("softmax_nchw_kernel");
+}
+
+extern "C" int cffm_upsample2_argmax(const float* scores, int64_t ldc, int64_t* labels, int B, int h, int w, int ncls,
+                                     int Hm, int Wm, int Ho, int Wo, void* stream) {
+  CFFM_REQUIRE(scores && labels, CFFM_E_BADARG, "upsample2_argmax: null pointer");
+  CFFM_REQUIRE(B > 0 && h > 0 && w > 0 && ncls > 0 && Hm > 0 && Wm > 0 && Ho > 0 && Wo > 0 && ldc >= ncls && B <= 65535,
+               CFFM_E_BADARG, "upsample2_argmax: bad size");
+  // intermediate rows/cols touched by a 16-pixel output tile: 16 * Hm/Ho + 3 (two taps + rounding)
+  const int need_y = (UP_TILE * Hm + Ho - 1) / Ho + 3, need_x = (UP_TILE * Wm + Wo - 1) / Wo + 3;
+  CFFM_REQUIRE(need_y <= UP_MT && need_x <= UP_MT, CFFM_E_UNSUPPORTED,
+               "upsample2_argmax: second stage must upsample by >= ~3.2x (tile needs %dx%d intermediate values, max %d)",
+               need_y, need_x, UP_MT);
+  const int smem = UP_MT * UP_MT * (ncls | 1) * 4;
+  CFFM_REQUIRE(smem <= 200 * 1024, CFFM_E_UNSUPPORTED, "upsample2_argmax: too many classes (%d)", ncls);
+  static cudaError_t e = cudaFuncSetAttribute(upsample2_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  CFFM_REQUIRE(e == cudaSuccess, -(int)e, "upsample2_argmax: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  dim3 grid((Wo + UP_TILE - 1) / UP_TILE, (Ho + UP_TILE - 1) / UP_TILE, B);
+  upsample2_argmax_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(scores, ldc, labels, h, w, ncls, Hm, Wm, Ho, Wo);
+  return launch_status("upsample2_argmax_kernel");
 }

@@ -1,13 +1,15 @@
 // out = act(A . W^T + bias) (+ residual) on the 5th-generation tensor cores.
 //
-// One 128 x BN output tile per CTA.  Warp-specialised:
+// Persistent, warp-specialised, one CTA per SM looping over 128 x BN output tiles:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzled [rows][64] fp16 stages)
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (accumulator in TMEM)
-//   warps 2..5  epilogue       (tcgen05.ld -> bias / GELU / ReLU / fp32 residual -> global)
-// Stage ring: full[s] (TMA -> MMA, transaction bytes) / empty[s] (tcgen05.commit -> TMA).
-// Two CTAs fit per SM (<= 97 KB smem, <= 128 TMEM columns each), so one CTA's epilogue
-// overlaps the other's main loop.  Tails in M, N and K are handled by TMA out-of-bounds
-// zero fill plus predicated stores.
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (2 accumulator stages in TMEM)
+//   warps 2..9  epilogue       (tcgen05.ld -> smem transpose -> bias / GELU / ReLU / fp32 residual ->
+//                               row-contiguous global stores), overlapped with the next tile's mainloop
+// Barriers: full[s] (TMA -> MMA, transaction bytes) / empty[s] (tcgen05.commit -> TMA),
+//           tfull[a] (tcgen05.commit -> epilogue) / tempty[a] (epilogue -> MMA).
+// Almost every GEMM of this path has K <= 256, i.e. it is HBM-bound: the design goal is bytes in
+// flight (4-6 TMA stages per SM) and fully coalesced epilogue traffic, not MMA issue rate.
+// Tails in M, N and K are handled by TMA out-of-bounds zero fill plus predicated stores.
 #include <cuda.h>
 
 #include <mutex>
@@ -21,8 +23,11 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // 64 halves = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;                  // two per TMEM lane quarter
+constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int STG_LD = 36;                        // padded fp32 row of the per-warp 32x32 transpose buffer
+constexpr int STG_BYTES = 32 * STG_LD * 4;
 
 struct Epilogue {
   const float* bias;
@@ -37,10 +42,11 @@ struct Epilogue {
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN == 64) ? 4 : 3;
+  static constexpr int STAGES = (BN == 64) ? 6 : 4;
   static constexpr int W_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + W_STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;        // double-buffered accumulator
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -49,10 +55,17 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// Persistent: grid = min(#tiles, #SMs); CTA c owns tiles c, c + grid, ... (n fastest, so the CTAs that
+// share an A row-panel run at the same time and the panel is read from HBM once).
+//   warp 0      TMA producer: smem ring of STAGES x (A 128x64 | W BNx64), runs ahead across tiles
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, accumulator stage = tile parity
+//   warps 2..9  epilogue: tcgen05.ld (thread = row) -> per-warp smem transpose -> row-contiguous
+//               128-byte global accesses for residual / fp32 / fp16; overlaps the next tile's mainloop
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                    const Epilogue ep, const int M, const int N, const int K) {
+                    const Epilogue ep, const int M, const int N, const int K, const int n_tiles_n,
+                    const int n_tiles) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -60,15 +73,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = smem_raw + pad;                              // 1024-byte aligned (SWIZZLE_128B atom)
   uint8_t* sA = smem;
   uint8_t* sW = smem + C::STAGES * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  float* stg_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + NUM_EPI_WARPS * STG_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tfull_bar = empty_bar + C::STAGES;                 // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;                        // [2] accumulator drained
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BLOCK_M;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
@@ -78,11 +91,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {                                             // whole warp: .sync.aligned
-    ptx::tmem_alloc(tmem_base_smem, BN);
+    ptx::tmem_alloc(tmem_base_smem, C::TMEM_COLS);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -93,80 +109,108 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % C::STAGES;
-        const uint32_t ph = (kb / C::STAGES) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);                // slot free (passes on the first round)
-        ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-        ptx::tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BLOCK_K, m0);
-        ptx::tma_load_2d(sW + s * C::W_STAGE_BYTES, &tmW, &full_bar[s], kb * BLOCK_K, n0);
+      uint32_t g = 0;                                          // k-blocks issued so far (all tiles)
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles_n) * BLOCK_M, n0 = (t % n_tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const uint32_t s = g % C::STAGES, ph = (g / C::STAGES) & 1u;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1u);              // slot free (passes on the first round)
+          ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          ptx::tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BLOCK_K, m0);
+          ptx::tma_load_2d(sW + s * C::W_STAGE_BYTES, &tmW, &full_bar[s], kb * BLOCK_K, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer (one thread) =====================
       constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % C::STAGES;
-        const uint32_t ph = (kb / C::STAGES) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);                      // TMA bytes have landed
+      uint32_t g = 0, it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+        ptx::mbar_wait(&tempty_bar[acc], aph ^ 1u);            // epilogue drained this accumulator stage
         ptx::tc_fence_after();
-        const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(sA + s * A_STAGE_BYTES));
-        const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(sW + s * C::W_STAGE_BYTES));
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const uint32_t s = g % C::STAGES, ph = (g / C::STAGES) & 1u;
+          ptx::mbar_wait(&full_bar[s], ph);                    // TMA bytes have landed
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(sA + s * A_STAGE_BYTES));
+          const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(sW + s * C::W_STAGE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advance 16 halves = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-          ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 halves = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+            ptx::umma_f16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);                     // frees the smem slot when the MMAs retire
         }
-        ptx::umma_commit(&empty_bar[s]);                       // frees the smem slot when the MMAs retire
+        ptx::umma_commit(&tfull_bar[acc]);                     // accumulator complete
       }
-      ptx::umma_commit(tmem_full_bar);                         // accumulator complete
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
+    // ===================== epilogue: TMEM -> regs -> smem transpose -> coalesced global =====================
+    const int ew = warp - 2;                                   // 0..7
     const int wq = warp & 3;                                   // TMEM lane quarter this warp may access
-    const int row = m0 + wq * 32 + lane;
-    const bool row_ok = row < M;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= N) break;                                 // warp-uniform
-      uint32_t v[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + c0, v);
+    const int chalf = ew >> 2;                                 // which 32-column chunks: c0/32 parity
+    float* stg = stg_all + ew * (32 * STG_LD);
+    const int rsub = lane >> 3, csub = (lane & 7) * 4;         // after the transpose: 4 rows x 8 float4 per pass
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int m0 = (t / n_tiles_n) * BLOCK_M, n0 = (t % n_tiles_n) * BN;
+      const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+      ptx::mbar_wait(&tfull_bar[acc], aph);
+      ptx::tc_fence_after();
+      constexpr int NCH = BN / 64;                             // chunks per warp
+      uint32_t v[NCH][32];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + (2 * c + chalf) * 32, v[c]);
       ptx::tmem_ld_wait();
-      if (row_ok) {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);       // registers hold the tile: MMA may reuse the stage
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = n0 + c0 + j * 8;
-          if (col < N) {                                       // N % 8 == 0: whole 8-wide chunk valid
-            float f[8];
+      for (int c = 0; c < NCH; ++c) {
+        const int col = n0 + (2 * c + chalf) * 32 + csub;      // this lane's 4 columns after the transpose
+        __syncwarp();
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
-            if (ep.bias != nullptr) {
-              const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + col);
-              const float4 b1 = *reinterpret_cast<const float4*>(ep.bias + col + 4);
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) =
+              make_float4(__uint_as_float(v[c][4 * j]), __uint_as_float(v[c][4 * j + 1]),
+                          __uint_as_float(v[c][4 * j + 2]), __uint_as_float(v[c][4 * j + 3]));
+        __syncwarp();
+        if (col < N) {                                         // N % 8 == 0: the float4 is all-valid or all-invalid
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias != nullptr) b4 = *reinterpret_cast<const float4*>(ep.bias + col);
+          const int rbase = m0 + wq * 32 + rsub;
+          float4 r4[8];
+          if (ep.residual != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = rbase + 4 * i;
+              r4[i] = row < M ? *reinterpret_cast<const float4*>(ep.residual + static_cast<int64_t>(row) * ep.ldr + col)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = rbase + 4 * i;
+            float4 a = *reinterpret_cast<const float4*>(stg + (rsub + 4 * i) * STG_LD + csub);
+            a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
             if (ep.act != CFFM_ACT_NONE) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = apply_act(f[e], ep.act);
+              a.x = apply_act(a.x, ep.act); a.y = apply_act(a.y, ep.act);
+              a.z = apply_act(a.z, ep.act); a.w = apply_act(a.w, ep.act);
             }
-            if (ep.residual != nullptr) {
-              const float* r = ep.residual + static_cast<int64_t>(row) * ep.ldr + col;
-              const float4 r0 = *reinterpret_cast<const float4*>(r);
-              const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
-              f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-              f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-            }
-            if (ep.out32 != nullptr) {
-              float* o = ep.out32 + static_cast<int64_t>(row) * ep.ldo32 + col;
-              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
-            }
-            if (ep.out16 != nullptr) {
-              *reinterpret_cast<half8*>(ep.out16 + static_cast<int64_t>(row) * ep.ldo16 + col) = pack8(f);
+            if (ep.residual != nullptr) { a.x += r4[i].x; a.y += r4[i].y; a.z += r4[i].z; a.w += r4[i].w; }
+            if (row < M) {
+              if (ep.out32 != nullptr)
+                *reinterpret_cast<float4*>(ep.out32 + static_cast<int64_t>(row) * ep.ldo32 + col) = a;
+              if (ep.out16 != nullptr) {
+                uint2 h;
+                h.x = pack_half2(a.x, a.y);
+                h.y = pack_half2(a.z, a.w);
+                *reinterpret_cast<uint2*>(ep.out16 + static_cast<int64_t>(row) * ep.ldo16 + col) = h;
+              }
             }
           }
         }
@@ -175,7 +219,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, BN);
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -240,6 +284,17 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 // 2-D fp16 row-major [rows, K] with row stride ld (elements); box = [box_rows][64], 128-byte swizzle.
 int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
@@ -271,8 +326,10 @@ int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const
                                     Cfg<BN>::SMEM_BYTES);
   });
   CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  dim3 grid((N + BN - 1) / BN, (M + BLOCK_M - 1) / BLOCK_M);
-  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmW, ep, M, N, K);
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int tiles = tiles_n * tiles_m;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmW, ep, M, N, K, tiles_n, tiles);
   return launch_status("gemm_tcgen05_kernel");
 }
 

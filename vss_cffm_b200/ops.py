@@ -156,6 +156,18 @@ def resize_argmax(logits, labels, B, ncls, h, w, Ho, Wo):
     _abi.call("cffm_resize_argmax", _ptr(logits), _ptr(labels), B, ncls, h, w, Ho, Wo, _stream())
 
 
+def upsample2_argmax(scores, ncls, labels, B, h, w, Hm, Wm, Ho, Wo):
+    """scores fp32 [B*h*w, ldc] NHWC -> two chained bilinear resizes -> argmax labels int64 [B,Ho,Wo]."""
+    _chk(scores, _F, "upsample2_argmax.scores")
+    assert scores.dim() == 2 and scores.shape[0] == B * h * w and scores.shape[1] >= ncls
+    assert labels.dtype == torch.int64 and labels.is_cuda and labels.is_contiguous() and labels.numel() == B * Ho * Wo
+    _abi.call("cffm_upsample2_argmax", _ptr(scores), _ld(scores), _ptr(labels), B, h, w, ncls, Hm, Wm, Ho, Wo, _stream())
+
+
+def upsample2_argmax_supported(Hm, Wm, Ho, Wo):
+    return (16 * Hm + Ho - 1) // Ho + 3 <= 8 and (16 * Wm + Wo - 1) // Wo + 3 <= 8
+
+
 def resize_nchw(x, out):
     _chk(x, _F, "resize_nchw.x"); _chk(out, _F, "resize_nchw.out")
     assert x.is_contiguous() and out.is_contiguous() and x.shape[:2] == out.shape[:2]
@@ -172,17 +184,22 @@ def softmax_nchw(x, out):
 
 class KernelTimer:
     """CUDA-event timing of selected entry points on the launching stream (bench.py's live roofline
-    measurement).  ``with KernelTimer({"cffm_cfm_attention"}) as kt: step()`` then ``kt.ms()``."""
+    measurement).  ``with KernelTimer({"cffm_cfm_attention"}) as kt: step()`` then ``kt.results()``."""
 
     def __init__(self, names):
         self.names = set(names)
-        self.events = {n: [] for n in self.names}
+        self.records = []                                        # (name, args, start_event, end_event)
+        self._open = None
 
-    def _hook(self, name, phase):
-        if name in self.names:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record(torch.cuda.current_stream())
-            self.events[name].append(ev)
+    def _hook(self, name, phase, args):
+        if name not in self.names:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        if phase == 0:
+            self._open = ev
+        else:
+            self.records.append((name, args, self._open, ev))
 
     def __enter__(self):
         _abi.launch_hook = self._hook
@@ -191,7 +208,7 @@ class KernelTimer:
     def __exit__(self, *exc):
         _abi.launch_hook = None
 
-    def ms(self):
-        """name -> list of per-launch durations (ms); synchronises."""
+    def results(self):
+        """list of (name, args, milliseconds) per timed launch; synchronises."""
         torch.cuda.synchronize()
-        return {n: [a.elapsed_time(b) for a, b in zip(ev[0::2], ev[1::2])] for n, ev in self.events.items()}
+        return [(n, a, s.elapsed_time(e)) for n, a, s, e in self.records]

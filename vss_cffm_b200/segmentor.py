@@ -118,14 +118,17 @@ class EncoderDecoder_clips(nn.Module):
             frames[t].copy_(f, non_blocking=True)
         return frames, B, T
 
+    def _features(self, frames, B, T):
+        """Backbone on frame-major frames; on the head's early-return path (eval and T != num_clips,
+        cffm_head.py:127-129) only the target frame influences the output, so only it is encoded."""
+        if T != self.decode_head.num_clips:
+            return self.extract_feat(frames[-1]), 1
+        return self.extract_feat(frames.reshape(T * B, *frames.shape[2:])), T
+
     def encode_decode_frames(self, frames, img_metas, B, T, **head_kw):
         """Backbone + head on frame-major frames (T,B,3,H,W) -> (B, num_classes, H/4, W/4) logits."""
-        head = self.decode_head
-        if T != head.num_clips:                                  # early return: only the target frame matters
-            x = self.extract_feat(frames[-1])
-            return head.forward_test(x, img_metas, self.test_cfg, B, 1, frame_major=True, **head_kw)
-        x = self.extract_feat(frames.reshape(T * B, *frames.shape[2:]))
-        return head.forward_test(x, img_metas, self.test_cfg, B, T, frame_major=True, **head_kw)
+        x, t = self._features(frames, B, T)
+        return self.decode_head.forward_test(x, img_metas, self.test_cfg, B, t, frame_major=True, **head_kw)
 
     def encode_decode(self, img, img_metas, batch_size, num_clips):
         """Reference signature (:367-378): img (B*T,3,H,W) clip-major -> logits resized to (H,W)."""
@@ -166,11 +169,31 @@ class EncoderDecoder_clips(nn.Module):
     def predict_labels(self, img, img_meta, rescale=True, **head_kw):
         """Device-side part of simple_test: int64 label maps (B,H,W) on the GPU."""
         frames, B, T = self._stack(img)
+        return self.labels_from_frames(frames, img_meta, rescale, **head_kw)
+
+    def labels_from_frames(self, frames, img_meta, rescale=True, **head_kw):
+        """frames: (T,B,3,H,W) fp32 on the device, frame-major -> int64 labels (B,H,W).  Pure sequence of
+        C-ABI launches on the current stream (no host sync, stable workspace addresses): CUDA-graph capturable."""
+        T, B = frames.shape[:2]
         H, W = frames.shape[-2:]
         ori = tuple(img_meta[0]["ori_shape"][:2])
         assert all(tuple(m["ori_shape"][:2]) == ori for m in img_meta)
-        logits = self.encode_decode_frames(frames, img_meta, B, T, **head_kw)     # (B,ncls,h,w)
-        h, w = logits.shape[2:]
+        head = self.decode_head
+        fused = (not (rescale and ori != (H, W))) and hasattr(head, "forward_scores")
+        if fused:
+            x, t = self._features(frames, B, T)
+            if "img_metas" not in head_kw:
+                head_kw = dict(head_kw, img_metas=img_meta)
+            scores, (hs, ws_), (h, w) = head.forward_scores(x, B, t, frame_major=True, **head_kw)
+            if ops.upsample2_argmax_supported(h, w, H, W):       # head's x2 resize + the x4 resize + argmax: one kernel
+                labels = torch.empty(B, H, W, dtype=torch.int64, device=scores.device)
+                ops.upsample2_argmax(scores, self.num_classes, labels, B, hs, ws_, h, w, H, W)
+                return self._flip(labels, img_meta)
+            logits = torch.empty(B, self.num_classes, h, w, dtype=_F, device=scores.device)
+            ops.resize_nhwc_to_nchw(scores, self.num_classes, logits, B, hs, ws_, h, w)
+        else:
+            logits = self.encode_decode_frames(frames, img_meta, B, T, **head_kw)     # (B,ncls,h,w)
+            h, w = logits.shape[2:]
         if rescale and ori != (H, W):                            # two chained resizes (:373-377 then :507-514)
             mid = torch.empty(B, self.num_classes, H, W, dtype=_F, device=logits.device)
             ops.resize_nchw(logits, mid)
@@ -178,6 +201,12 @@ class EncoderDecoder_clips(nn.Module):
         labels = torch.empty(B, H, W, dtype=torch.int64, device=logits.device)
         ops.resize_argmax(logits, labels, B, self.num_classes, h, w, H, W)
         return self._flip(labels, img_meta)
+
+    def make_graphed(self, B, T, H, W, img_meta=None, rescale=True, **head_kw):
+        """Capture one inference pass for fixed (B,T,H,W) in a CUDA graph: the ~130 kernel launches of a step are
+        replayed with one cudaGraphLaunch, removing the host launch overhead.  Returns a ``GraphedClips``."""
+        from .graph import GraphedClips
+        return GraphedClips(self, B, T, H, W, img_meta, rescale, head_kw)
 
     def simple_test(self, img, img_meta, rescale=True, **head_kw):
         """encoder_decoder.py:554-572: list of B (H,W) int64 numpy label maps."""
