@@ -13,6 +13,13 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CFFM_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 }  // namespace cffm
 
 extern "C" int cffm_abi_version(void) { return CFFM_ABI_VERSION; }

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256)
 mha_small_kv_kernel(const __half* __restrict__ q, int64_t ldq, const __half* __restrict__ k,
                     const __half* __restrict__ v, int64_t ldkv, __half* __restrict__ out, int64_t ldo, int Nq, int Nkv,
                     int nkv_pad, float scale_log2e) {
+  pdl_sync();
   constexpr int LD = D + 8;                                 // padded smem row (halves): conflict-free LDS/ldmatrix
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __half* Ks = reinterpret_cast<__half*>(smem_raw);
@@ -50,8 +51,14 @@ mha_small_kv_kernel(const __half* __restrict__ q, int64_t ldq, const __half* __r
   }
   ptx::cp_async_commit();
 
-  // ---- Q fragments straight from global (each warp owns 16 query rows)
-  const int r0 = blockIdx.x * 128 + warp * 16;
+  ptx::cp_async_wait_all();
+  __syncthreads();
+  const uint32_t vs_addr = ptx::smem_u32(Vs);
+  // ---- loop over 128-query tiles: K/V of this (batch, head) stay resident in shared memory
+  for (int qt = blockIdx.x; qt * 128 < Nq; qt += gridDim.x) {
+  // Q fragments straight from global (each warp owns 16 query rows)
+  const int r0 = qt * 128 + warp * 16;
+  if (r0 >= Nq) continue;                                   // warp-uniform; no block syncs inside the loop
   const int rowA = r0 + g, rowB = r0 + g + 8;
   const __half* qA = q + (static_cast<int64_t>(b) * Nq + rowA) * ldq + h * D;
   const __half* qB = q + (static_cast<int64_t>(b) * Nq + rowB) * ldq + h * D;
@@ -63,15 +70,10 @@ mha_small_kv_kernel(const __half* __restrict__ q, int64_t ldq, const __half* __r
     a[kk][2] = rowA < Nq ? *reinterpret_cast<const uint32_t*>(qA + kk * 16 + 8 + 2 * t) : 0u;
     a[kk][3] = rowB < Nq ? *reinterpret_cast<const uint32_t*>(qB + kk * 16 + 8 + 2 * t) : 0u;
   }
-  ptx::cp_async_wait_all();
-  __syncthreads();
-  if (r0 >= Nq) return;                                     // warp-uniform; no further block syncs
-
   float o[D / 8][4];
 #pragma unroll
   for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;
-  const uint32_t vs_addr = ptx::smem_u32(Vs);
 
   for (int c = 0; c < nkv_pad; c += 64) {
     float s[8][4];
@@ -143,6 +145,7 @@ mha_small_kv_kernel(const __half* __restrict__ q, int64_t ldq, const __half* __r
     if (rowA < Nq) *reinterpret_cast<uint32_t*>(oA + nd * 8 + 2 * t) = pack_half2(o[nd][0] * iA, o[nd][1] * iA);
     if (rowB < Nq) *reinterpret_cast<uint32_t*>(oB + nd * 8 + 2 * t) = pack_half2(o[nd][2] * iB, o[nd][3] * iB);
   }
+  }                                                         // query-tile loop
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -192,6 +195,7 @@ __device__ __forceinline__ KeySrc cfm_key_source(int n, int wi, int wj, int nWh,
 }
 
 __global__ void cfm_key_sources_kernel(int Hp, int Wp, int32_t* out) {
+  pdl_sync();
   const int nWh = Hp / WS, nWw = Wp / WS;
   const int w = blockIdx.x, n = threadIdx.x;
   if (n >= NKEYS) return;
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(128)
 cfm_attention_kernel(const __half* __restrict__ qkv_t, const __half* __restrict__ kv_pooled,
                      const float* __restrict__ bias, __half* __restrict__ out, int H, int W, int Hp, int Wp, int P,
                      float scale) {
+  pdl_sync();
   constexpr int D = 32, C = 256, LD = D + 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __half* Ks = reinterpret_cast<__half*>(smem_raw);
@@ -389,17 +394,22 @@ extern "C" int cffm_mha_f16(const void* q, int64_t ldq, const void* k, const voi
   const int smem = 2 * nkv_pad * (head_dim + 8) * 2;
   CFFM_REQUIRE(smem <= 200 * 1024, CFFM_E_UNSUPPORTED, "mha: Nkv=%d does not fit in shared memory", Nkv);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid((Nq + 127) / 128, heads, batch);
+  // enough CTAs for ~2 per SM; each loops over query tiles so that the K/V staging is amortised
+  const int qtiles = (Nq + 127) / 128;
+  int gx = (2 * 148 + heads * batch - 1) / (heads * batch);
+  if (gx > qtiles) gx = qtiles;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, heads, batch);
   const float sl = scale * 1.4426950408889634f;
   int rc;
   if (head_dim == 64) {
     if ((rc = set_smem_attr<mha_small_kv_kernel<64>>())) return rc;
-    mha_small_kv_kernel<64><<<grid, 256, smem, st>>>(static_cast<const __half*>(q), ldq, static_cast<const __half*>(k),
+    launch_k(mha_small_kv_kernel<64>, grid, 256, smem, st, static_cast<const __half*>(q), ldq, static_cast<const __half*>(k),
                                                      static_cast<const __half*>(v), ldkv, static_cast<__half*>(out),
                                                      ldo, Nq, Nkv, nkv_pad, sl);
   } else {
     if ((rc = set_smem_attr<mha_small_kv_kernel<32>>())) return rc;
-    mha_small_kv_kernel<32><<<grid, 256, smem, st>>>(static_cast<const __half*>(q), ldq, static_cast<const __half*>(k),
+    launch_k(mha_small_kv_kernel<32>, grid, 256, smem, st, static_cast<const __half*>(q), ldq, static_cast<const __half*>(k),
                                                      static_cast<const __half*>(v), ldkv, static_cast<__half*>(out),
                                                      ldo, Nq, Nkv, nkv_pad, sl);
   }
@@ -422,7 +432,7 @@ extern "C" int cffm_cfm_attention(const void* qkv_t, const void* kv_pooled, cons
   int rc = set_smem_attr<cfm_attention_kernel>();
   if (rc) return rc;
   dim3 grid(nW, heads, B);
-  cfm_attention_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(cfm_attention_kernel, grid, 128, smem, static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(qkv_t), static_cast<const __half*>(kv_pooled), bias, static_cast<__half*>(out), H, W,
       Hp, Wp, 15 * nW, scale);
   return launch_status("cfm_attention_kernel");
@@ -432,6 +442,6 @@ extern "C" int cffm_cfm_key_sources(int Hp, int Wp, int32_t* out, void* stream) 
   using namespace cffm;
   CFFM_REQUIRE(out && Hp > 0 && Wp > 0 && Hp % WS == 0 && Wp % WS == 0, CFFM_E_BADARG,
                "cfm_key_sources: Hp, Wp must be positive multiples of 7");
-  cfm_key_sources_kernel<<<(Hp / WS) * (Wp / WS), 320, 0, static_cast<cudaStream_t>(stream)>>>(Hp, Wp, out);
+  launch_k(cfm_key_sources_kernel, (Hp / WS) * (Wp / WS), 320, 0, static_cast<cudaStream_t>(stream), Hp, Wp, out);
   return launch_status("cfm_key_sources_kernel");
 }

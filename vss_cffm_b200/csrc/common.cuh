@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/cffm_b200.h"
 
@@ -27,6 +28,33 @@ inline int launch_status(const char* what) {
     return -(int)e;
   }
   return CFFM_OK;
+}
+
+// ---- programmatic dependent launch (PDL).  Every kernel of this library is launched with the
+// programmatic-stream-serialization attribute and starts with pdl_sync(): it lets the NEXT kernel's CTAs be
+// scheduled (launch latency + prologue overlap this kernel's execution) and then blocks until the PREVIOUS
+// kernel has completed and flushed, before the first global-memory access.  Works inside CUDA-graph capture.
+// CFFM_PDL=0 in the environment falls back to plain stream-ordered launches.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // status is read by launch_status()
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ xin, int64_t ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ o16, int64_t ldo16,
                  float* __restrict__ o32, int64_t ldo32, int M, int C) {
+  pdl_sync();
   constexpr int RPW = 32 / L;                                  // rows per warp
   const int lane = threadIdx.x & 31;
   const int gl = lane % L;                                     // lane inside the row group
@@ -104,6 +105,7 @@ layernorm_kernel(const void* __restrict__ xin, int64_t ldx, const float* __restr
 __global__ void __launch_bounds__(256)
 im2col_nhwc_kernel(const __half* __restrict__ x, int N, int H, int W, int C, int k, int stride, int pad, int Ho,
                    int Wo, __half* __restrict__ A, int Kpad) {
+  pdl_sync();
   const int chunks = Kpad / 8;
   const int64_t total = static_cast<int64_t>(N) * Ho * Wo * chunks;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
@@ -129,34 +131,45 @@ im2col_nhwc_kernel(const __half* __restrict__ x, int N, int H, int W, int C, int
 __global__ void __launch_bounds__(256)
 im2col_nchw_f32_kernel(const float* __restrict__ x, int N, int H, int W, int C, int k, int stride, int pad, int Ho,
                        int Wo, __half* __restrict__ A, int Kpad) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t im_smem[];
-  __half* rows = reinterpret_cast<__half*>(im_smem);           // [C][k][Wp], Wp = W + 2*pad (zero borders)
   const int Wp = W + 2 * pad;
+  const int kdim = k * k * C, chunks = Kpad / 8;
+  __half* rows = reinterpret_cast<__half*>(im_smem);           // [C*k][Wp] (zero borders)
+  int* lut = reinterpret_cast<int*>(im_smem + ((static_cast<size_t>(C) * k * Wp * 2 + 15) & ~static_cast<size_t>(15)));   // [Kpad]
   const int oy = blockIdx.x % Ho, n = blockIdx.x / Ho;
-  for (int i = threadIdx.x; i < C * k * Wp; i += 256) {
-    const int xx = i % Wp - pad, ky = (i / Wp) % k, c = i / (Wp * k);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int kc = threadIdx.x; kc < Kpad; kc += 256) {          // patch column -> offset inside `rows` (-1: zero pad)
+    int off = -1;
+    if (kc < kdim) {
+      const int c = kc % C, tap = kc / C, kx = tap % k, ky = tap / k;
+      off = (c * k + ky) * Wp + kx;
+    }
+    lut[kc] = off;
+  }
+  for (int r = warp; r < C * k; r += 8) {                      // one (channel, ky) input row per warp pass
+    const int ky = r % k, c = r / k;
     const int iy = oy * stride - pad + ky;
-    float v = 0.f;
-    if (xx >= 0 && xx < W && iy >= 0 && iy < H) v = x[((static_cast<int64_t>(n) * C + c) * H + iy) * W + xx];
-    rows[i] = __float2half_rn(v);
+    const bool rv = iy >= 0 && iy < H;
+    const float* src = x + ((static_cast<int64_t>(n) * C + c) * H + (rv ? iy : 0)) * W;
+    for (int xp = lane; xp < Wp; xp += 32) {
+      const int xx = xp - pad;
+      rows[r * Wp + xp] = __float2half_rn(rv && xx >= 0 && xx < W ? src[xx] : 0.f);
+    }
   }
   __syncthreads();
-  const int chunks = Kpad / 8, kdim = k * k * C;
   __half* Arow = A + (static_cast<int64_t>(n) * Ho + oy) * Wo * Kpad;
-  for (int i = threadIdx.x; i < Wo * chunks; i += 256) {
-    const int ch = i % chunks, ox = i / chunks;
-    __align__(16) __half v[8];
+  for (int ox = warp; ox < Wo; ox += 8) {                      // one output pixel per warp pass, lanes over 16-byte chunks
+    const __half* rbase = rows + ox * stride;
+    for (int ch = lane; ch < chunks; ch += 32) {
+      __align__(16) __half v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int kc = ch * 8 + e;
-      __half h = __float2half_rn(0.f);
-      if (kc < kdim) {
-        const int c = kc % C, tap = kc / C, kx = tap % k, ky = tap / k;
-        h = rows[(c * k + ky) * Wp + ox * stride + kx];
+      for (int e = 0; e < 8; ++e) {
+        const int off = lut[ch * 8 + e];
+        v[e] = off >= 0 ? rbase[off] : __float2half_rn(0.f);
       }
-      v[e] = h;
+      *reinterpret_cast<uint4*>(Arow + static_cast<int64_t>(ox) * Kpad + ch * 8) = *reinterpret_cast<const uint4*>(v);
     }
-    *reinterpret_cast<uint4*>(Arow + static_cast<int64_t>(ox) * Kpad + ch * 8) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
@@ -168,6 +181,7 @@ constexpr int DW_PX = 4;
 __global__ void __launch_bounds__(256)
 dwconv3x3_gelu_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
                       __half* __restrict__ out, int N, int H, int W, int C) {
+  pdl_sync();
   const int chunks = C / 8, strips = (W + DW_PX - 1) / DW_PX;
   const int64_t total = static_cast<int64_t>(N) * H * strips * chunks;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
@@ -249,6 +263,7 @@ head_fuse_kernel(const __half* __restrict__ p1, const __half* __restrict__ p2, c
                  const __half* __restrict__ p4, int N, int H1, int W1, int H2, int W2, int H3, int W3, int H4, int W4,
                  int C, int Tperm, const float* __restrict__ shift, __half* __restrict__ c_full,
                  float* __restrict__ h32, int64_t ldh32, __half* __restrict__ h16, int64_t ldh16) {
+  pdl_sync();
   const int chunks = C / 8, Hh = H1 / 2, Wh = W1 / 2;
   const int64_t total = static_cast<int64_t>(N) * Hh * Wh * chunks;
   const float sy2 = static_cast<float>(H2) / H1, sx2 = static_cast<float>(W2) / W1;
@@ -306,6 +321,7 @@ __global__ void __launch_bounds__(256)
 cffa_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, __half* __restrict__ xn, __half* __restrict__ xt_pad, int B, int T, int H, int W, int Hp,
                  int Wp) {
+  pdl_sync();
   constexpr int C = 256;
   const int64_t tok = blockIdx.x * 8ll + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -340,6 +356,7 @@ cffa_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 __global__ void __launch_bounds__(256)
 cffa_pool_kernel(const __half* __restrict__ xn, int B, int T, int H, int W, int Hp, int Wp,
                  const float* __restrict__ pool_w, const float* __restrict__ pool_b, __half* __restrict__ pooled) {
+  pdl_sync();
   constexpr int C = 256, WS = 7;
   const int nWh = Hp / WS, nWw = Wp / WS, nW = nWh * nWw, P = 15 * nW;
   const int64_t gw = blockIdx.x * 8ll + (threadIdx.x >> 5);
@@ -358,15 +375,21 @@ cffa_pool_kernel(const __half* __restrict__ xn, int B, int T, int H, int W, int 
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   if (level < 2) {                                            // 7x7 fc-pool on the zero-padded map itself
+#pragma unroll
     for (int u = 0; u < WS; ++u) {
       const int y = WS * py + u;
-      if (y >= H) break;
-      for (int v = 0; v < WS; ++v) {
+      half8 row[WS];
+#pragma unroll
+      for (int v = 0; v < WS; ++v) {                              // 7 independent loads in flight
         const int xx = WS * px + v;
-        if (xx >= W) break;
+        if (y < H && xx < W) row[v] = *reinterpret_cast<const half8*>(src + (static_cast<int64_t>(y) * W + xx) * C);
+        else row[v].h[0] = row[v].h[1] = row[v].h[2] = row[v].h[3] = __floats2half2_rn(0.f, 0.f);
+      }
+#pragma unroll
+      for (int v = 0; v < WS; ++v) {
         const float wt = pool_w[woff + u * WS + v];
         float t[8];
-        unpack8(*reinterpret_cast<const half8*>(src + (static_cast<int64_t>(y) * W + xx) * C), t);
+        unpack8(row[v], t);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = fmaf(wt, t[e], acc[e]);
       }
@@ -407,6 +430,7 @@ template <bool IN_F32>
 __global__ void __launch_bounds__(256)
 resize_nhwc_to_nchw_kernel(const void* __restrict__ in, int64_t ldc, float* __restrict__ out, int B, int h, int w,
                            int ncls, int Ho, int Wo) {
+  pdl_sync();
   const int64_t total = static_cast<int64_t>(B) * Ho * Wo;
   const float sy = static_cast<float>(h) / Ho, sx = static_cast<float>(w) / Wo;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
@@ -434,6 +458,7 @@ resize_nhwc_to_nchw_kernel(const void* __restrict__ in, int64_t ldc, float* __re
 __global__ void __launch_bounds__(256)
 resize_argmax_kernel(const float* __restrict__ logits, int64_t* __restrict__ labels, int B, int ncls, int h, int w,
                      int Ho, int Wo) {
+  pdl_sync();
   const int64_t total = static_cast<int64_t>(B) * Ho * Wo;
   const float sy = static_cast<float>(h) / Ho, sx = static_cast<float>(w) / Wo;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
@@ -455,6 +480,7 @@ resize_argmax_kernel(const float* __restrict__ logits, int64_t* __restrict__ lab
 // plain fp32 NCHW -> NCHW bilinear resize (whole_inference rescale step)
 __global__ void __launch_bounds__(256)
 resize_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t planes, int h, int w, int Ho, int Wo) {
+  pdl_sync();
   const int64_t total = planes * Ho * Wo;
   const float sy = static_cast<float>(h) / Ho, sx = static_cast<float>(w) / Wo;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
@@ -470,6 +496,7 @@ resize_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int64_
 // softmax over the channel dimension of fp32 NCHW; one thread per pixel (coalesced along W)
 __global__ void __launch_bounds__(256)
 softmax_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int64_t HW) {
+  pdl_sync();
   const int64_t total = static_cast<int64_t>(B) * HW;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
     const int64_t b = i / HW, px = i % HW;
@@ -493,6 +520,7 @@ constexpr int UP_TILE = 16, UP_MT = 8;
 __global__ void __launch_bounds__(256)
 upsample2_argmax_kernel(const float* __restrict__ lg, int64_t ldc, int64_t* __restrict__ labels, int h, int w,
                         int ncls, int Hm, int Wm, int Ho, int Wo) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t up_smem[];
   float* mid = reinterpret_cast<float*>(up_smem);              // [UP_MT*UP_MT][CP], CP odd -> conflict-free
   const int CP = ncls | 1;
@@ -546,7 +574,7 @@ static void launch_ln(const void* x, int64_t ldx, const float* gamma, const floa
   int64_t grid = (warps + 7) / 8;
   const int64_t cap = 148 * 8 * 4;                             // 8 resident CTAs per SM, a few rows per warp
   if (grid > cap) grid = cap;
-  layernorm_kernel<F32, L, NV><<<static_cast<int>(grid), 256, 0, st>>>(x, ldx, gamma, beta, eps, o16, ldo16, o32, ldo32, M, C);
+  launch_k(layernorm_kernel<F32, L, NV>, static_cast<int>(grid), 256, 0, st, x, ldx, gamma, beta, eps, o16, ldo16, o32, ldo32, M, C);
 }
 
 extern "C" int cffm_layernorm(const void* x, int x_is_f32, int64_t ldx, const float* gamma, const float* beta,
@@ -587,16 +615,16 @@ extern "C" int cffm_im2col(const void* x, int layout, int N, int H, int W, int C
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (layout == 1) {
     CFFM_REQUIRE(C % 8 == 0 && aligned16(x) && aligned16(A), CFFM_E_UNSUPPORTED, "im2col: NHWC path needs C %% 8 == 0");
-    im2col_nhwc_kernel<<<grid_for(static_cast<int64_t>(N) * Ho * Wo * (Kpad / 8)), 256, 0, st>>>(
+    launch_k(im2col_nhwc_kernel, grid_for(static_cast<int64_t>(N) * Ho * Wo * (Kpad / 8)), 256, 0, st, 
         static_cast<const __half*>(x), N, H, W, C, k, stride, pad, Ho, Wo, static_cast<__half*>(A), Kpad);
   } else {
     CFFM_REQUIRE(layout == 0, CFFM_E_BADARG, "im2col: bad layout %d", layout);
-    const int smem = C * k * (W + 2 * pad) * 2;
+    const int smem = ((C * k * (W + 2 * pad) * 2 + 15) & ~15) + Kpad * 4;
     CFFM_REQUIRE(smem <= 200 * 1024 && aligned16(A), CFFM_E_UNSUPPORTED,
                  "im2col: NCHW path stages C*k*(W+2*pad) halves (%d bytes) in shared memory", smem);
     static cudaError_t e = cudaFuncSetAttribute(im2col_nchw_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     CFFM_REQUIRE(e == cudaSuccess, -(int)e, "im2col: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    im2col_nchw_f32_kernel<<<N * Ho, 256, smem, st>>>(static_cast<const float*>(x), N, H, W, C, k, stride, pad, Ho, Wo,
+    launch_k(im2col_nchw_f32_kernel, N * Ho, 256, smem, st, static_cast<const float*>(x), N, H, W, C, k, stride, pad, Ho, Wo,
                                                        static_cast<__half*>(A), Kpad);
   }
   return launch_status("im2col_kernel");
@@ -607,7 +635,7 @@ extern "C" int cffm_dwconv3x3_gelu(const void* x, const void* w, const float* bi
   CFFM_REQUIRE(x && w && bias && out, CFFM_E_BADARG, "dwconv: null pointer");
   CFFM_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, CFFM_E_UNSUPPORTED, "dwconv: need C %% 8 == 0");
   CFFM_REQUIRE(aligned16(x) && aligned16(w) && aligned16(bias) && aligned16(out), CFFM_E_BADARG, "dwconv: misaligned");
-  dwconv3x3_gelu_kernel<<<grid_for(static_cast<int64_t>(N) * H * ((W + DW_PX - 1) / DW_PX) * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(dwconv3x3_gelu_kernel, grid_for(static_cast<int64_t>(N) * H * ((W + DW_PX - 1) / DW_PX) * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(x), static_cast<const __half*>(w), bias, static_cast<__half*>(out), N, H, W, C);
   return launch_status("dwconv3x3_gelu_kernel");
 }
@@ -623,7 +651,7 @@ extern "C" int cffm_head_fuse(const void* p1, const void* p2, const void* p3, co
   CFFM_REQUIRE(C % 8 == 0 && H1 % 2 == 0 && W1 % 2 == 0, CFFM_E_UNSUPPORTED, "head_fuse: need C %% 8 == 0 and even H1, W1");
   CFFM_REQUIRE((!c_half_f32 || ldh32 % 4 == 0) && (!c_half_f16 || ldh16 % 8 == 0), CFFM_E_BADARG, "head_fuse: bad stride");
   CFFM_REQUIRE(T_perm >= 0 && (T_perm <= 1 || N % T_perm == 0), CFFM_E_BADARG, "head_fuse: N=%d not a multiple of T_perm=%d", N, T_perm);
-  head_fuse_kernel<<<grid_for(static_cast<int64_t>(N) * (H1 / 2) * (W1 / 2) * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(head_fuse_kernel, grid_for(static_cast<int64_t>(N) * (H1 / 2) * (W1 / 2) * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(p1), static_cast<const __half*>(p2), static_cast<const __half*>(p3),
       static_cast<const __half*>(p4), N, H1, W1, H2, W2, H3, W3, H4, W4, C, T_perm, shift, static_cast<__half*>(c_full),
       c_half_f32, ldh32, static_cast<__half*>(c_half_f16), ldh16);
@@ -636,7 +664,7 @@ extern "C" int cffm_cffa_norm(const float* x, const float* gamma, const float* b
   CFFM_REQUIRE(B > 0 && T > 0 && H > 0 && W > 0 && Hp >= H && Wp >= W, CFFM_E_BADARG, "cffa_norm: bad size");
   CFFM_REQUIRE(C == 256, CFFM_E_UNSUPPORTED, "cffa_norm: built for C=256, got %d", C);
   const int64_t tokens = static_cast<int64_t>(B) * T * H * W;
-  cffa_norm_kernel<<<static_cast<int>((tokens + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(cffa_norm_kernel, static_cast<int>((tokens + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
       x, gamma, beta, eps, static_cast<__half*>(xn), static_cast<__half*>(xt_pad), B, T, H, W, Hp, Wp);
   return launch_status("cffa_norm_kernel");
 }
@@ -649,7 +677,7 @@ extern "C" int cffm_cffa_pool(const void* xn, int B, int T, int H, int W, int C,
                "cffa_pool: built for C=256 and T=4 (3 reference frames, focal_l_clips=[1,2,3]); got C=%d T=%d", C, T);
   const int Hp = (H + 6) / 7 * 7, Wp = (W + 6) / 7 * 7;
   const int64_t warps = static_cast<int64_t>(B) * 15 * (Hp / 7) * (Wp / 7);
-  cffa_pool_kernel<<<static_cast<int>((warps + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(cffa_pool_kernel, static_cast<int>((warps + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(xn), B, T, H, W, Hp, Wp, pool_w, pool_b, static_cast<__half*>(pooled));
   return launch_status("cffa_pool_kernel");
 }
@@ -660,8 +688,8 @@ extern "C" int cffm_resize_nhwc_to_nchw(const void* in, int in_is_f32, int64_t l
   CFFM_REQUIRE(B > 0 && h > 0 && w > 0 && ncls > 0 && Ho > 0 && Wo > 0 && ldc >= ncls, CFFM_E_BADARG, "resize: bad size");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = grid_for(static_cast<int64_t>(B) * Ho * Wo);
-  if (in_is_f32) resize_nhwc_to_nchw_kernel<true><<<grid, 256, 0, st>>>(in, ldc, out, B, h, w, ncls, Ho, Wo);
-  else resize_nhwc_to_nchw_kernel<false><<<grid, 256, 0, st>>>(in, ldc, out, B, h, w, ncls, Ho, Wo);
+  if (in_is_f32) launch_k(resize_nhwc_to_nchw_kernel<true>, grid, 256, 0, st, in, ldc, out, B, h, w, ncls, Ho, Wo);
+  else launch_k(resize_nhwc_to_nchw_kernel<false>, grid, 256, 0, st, in, ldc, out, B, h, w, ncls, Ho, Wo);
   return launch_status("resize_nhwc_to_nchw_kernel");
 }
 
@@ -669,7 +697,7 @@ extern "C" int cffm_resize_argmax(const float* logits, int64_t* labels, int B, i
                                   void* stream) {
   CFFM_REQUIRE(logits && labels, CFFM_E_BADARG, "resize_argmax: null pointer");
   CFFM_REQUIRE(B > 0 && ncls > 0 && h > 0 && w > 0 && Ho > 0 && Wo > 0, CFFM_E_BADARG, "resize_argmax: bad size");
-  resize_argmax_kernel<<<grid_for(static_cast<int64_t>(B) * Ho * Wo), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(resize_argmax_kernel, grid_for(static_cast<int64_t>(B) * Ho * Wo), 256, 0, static_cast<cudaStream_t>(stream), 
       logits, labels, B, ncls, h, w, Ho, Wo);
   return launch_status("resize_argmax_kernel");
 }
@@ -678,14 +706,14 @@ extern "C" int cffm_resize_nchw(const float* in, float* out, int B, int C, int h
   CFFM_REQUIRE(in && out, CFFM_E_BADARG, "resize_nchw: null pointer");
   CFFM_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0 && Ho > 0 && Wo > 0, CFFM_E_BADARG, "resize_nchw: bad size");
   const int64_t planes = static_cast<int64_t>(B) * C;
-  resize_nchw_kernel<<<grid_for(planes * Ho * Wo), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, planes, h, w, Ho, Wo);
+  launch_k(resize_nchw_kernel, grid_for(planes * Ho * Wo), 256, 0, static_cast<cudaStream_t>(stream), in, out, planes, h, w, Ho, Wo);
   return launch_status("resize_nchw_kernel");
 }
 
 extern "C" int cffm_softmax_nchw(const float* in, float* out, int B, int C, int64_t HW, void* stream) {
   CFFM_REQUIRE(in && out, CFFM_E_BADARG, "softmax_nchw: null pointer");
   CFFM_REQUIRE(B > 0 && C > 0 && HW > 0, CFFM_E_BADARG, "softmax_nchw: bad size");
-  softmax_nchw_kernel<<<grid_for(static_cast<int64_t>(B) * HW), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, B, C, HW);
+  launch_k(softmax_nchw_kernel, grid_for(static_cast<int64_t>(B) * HW), 256, 0, static_cast<cudaStream_t>(stream), in, out, B, C, HW);
   return launch_status("softmax_nchw_kernel");
 }
 
@@ -704,6 +732,6 @@ extern "C" int cffm_upsample2_argmax(const float* scores, int64_t ldc, int64_t* 
   static cudaError_t e = cudaFuncSetAttribute(upsample2_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   CFFM_REQUIRE(e == cudaSuccess, -(int)e, "upsample2_argmax: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   dim3 grid((Wo + UP_TILE - 1) / UP_TILE, (Ho + UP_TILE - 1) / UP_TILE, B);
-  upsample2_argmax_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(scores, ldc, labels, h, w, ncls, Hm, Wm, Ho, Wo);
+  launch_k(upsample2_argmax_kernel, grid, 256, smem, static_cast<cudaStream_t>(stream), scores, ldc, labels, h, w, ncls, Hm, Wm, Ho, Wo);
   return launch_status("upsample2_argmax_kernel");
 }

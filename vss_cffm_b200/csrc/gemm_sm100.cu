@@ -13,6 +13,7 @@
 #include <cuda.h>
 
 #include <mutex>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -27,7 +28,7 @@ constexpr int NUM_EPI_WARPS = 8;                  // two per TMEM lane quarter
 constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int STG_LD = 36;                        // padded fp32 row of the per-warp 32x32 transpose buffer
-constexpr int STG_BYTES = 32 * STG_LD * 4;
+constexpr int STG_BYTES = 32 * STG_LD * 4 + 768;   // 32x36 fp32 transpose buffer (or 32 x 144 B fp16 rows) + bias slice
 
 struct Epilogue {
   const float* bias;
@@ -61,7 +62,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, accumulator stage = tile parity
 //   warps 2..9  epilogue: tcgen05.ld (thread = row) -> per-warp smem transpose -> row-contiguous
 //               128-byte global accesses for residual / fp32 / fp16; overlaps the next tile's mainloop
-template <int BN>
+template <int BN, bool F16_ONLY>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const Epilogue ep, const int M, const int N, const int K, const int n_tiles_n,
@@ -83,6 +84,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int dbg = ep.act >> 8;                                 // 0 in production
+  const int act = ep.act & 0xff;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -105,6 +108,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  pdl_sync();                                                  // prologue above overlaps the previous kernel
 
   if (warp == 0) {
     if (lane == 0) {
@@ -115,6 +119,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb, ++g) {
           const uint32_t s = g % C::STAGES, ph = (g / C::STAGES) & 1u;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1u);              // slot free (passes on the first round)
+          if (dbg & 4) {                                       // probe: W only
+            ptx::mbar_arrive_expect_tx(&full_bar[s], C::W_STAGE_BYTES);
+            ptx::tma_load_2d(sW + s * C::W_STAGE_BYTES, &tmW, &full_bar[s], kb * BLOCK_K, n0);
+            continue;
+          }
           ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
           ptx::tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BLOCK_K, m0);
           ptx::tma_load_2d(sW + s * C::W_STAGE_BYTES, &tmW, &full_bar[s], kb * BLOCK_K, n0);
@@ -149,29 +158,111 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ===================== epilogue: TMEM -> regs -> smem transpose -> coalesced global =====================
+    // Warp (quarter wq, half ch) owns rows [32 wq, +32) x columns [ch BN/2, +BN/2) of the tile.  Everything that
+    // does not depend on the accumulator (bias, residual) is fetched BEFORE waiting for the MMA.
     const int ew = warp - 2;                                   // 0..7
     const int wq = warp & 3;                                   // TMEM lane quarter this warp may access
-    const int chalf = ew >> 2;                                 // which 32-column chunks: c0/32 parity
-    float* stg = stg_all + ew * (32 * STG_LD);
-    const int rsub = lane >> 3, csub = (lane & 7) * 4;         // after the transpose: 4 rows x 8 float4 per pass
+    const int ch = ew >> 2;                                    // column half of the tile
+    constexpr int NCH = BN / 64;                               // 32-column chunks per warp (adjacent)
+    constexpr int WCOLS = NCH * 32;                            // columns per warp
+    uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg_all) + ew * STG_BYTES;
+    float* stg = reinterpret_cast<float*>(stg8);
+    float* sbias = reinterpret_cast<float*>(stg8 + STG_BYTES - 256);   // [WCOLS <= 64] bias slice of this warp
     uint32_t it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int m0 = (t / n_tiles_n) * BLOCK_M, n0 = (t % n_tiles_n) * BN;
+      const int wcol0 = n0 + ch * WCOLS;                       // first column of this warp
+      const int wrow0 = m0 + wq * 32;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+      if (F16_ONLY) {
+        // ---- fp16-only output (q / kv / qkv / fc1 / folded decoder projections)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int col = wcol0 + 32 * c + lane;
+          sbias[32 * c + lane] = (ep.bias != nullptr && col < N) ? __ldg(ep.bias + col) : 0.f;
+        }
+        __syncwarp();
+        ptx::mbar_wait(&tfull_bar[acc], aph);
+        ptx::tc_fence_after();
+        uint32_t v[NCH][32];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+          ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + ch * WCOLS + 32 * c, v[c]);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);     // registers hold the tile: MMA may reuse the stage
+        if (dbg & 2) continue;                                 // probe: no epilogue work at all
+        // bias + activation in the thread = row layout (bias is warp-uniform: broadcast LDS), pack to fp16 and
+        // stage [32 rows][WCOLS halves]; then each row is written with 16-byte lanes (WCOLS*2 contiguous bytes).
+        constexpr int P16 = WCOLS * 2 + 16;                    // padded row pitch (bytes): conflict-free STS.128
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b0 = *reinterpret_cast<const float4*>(sbias + 32 * c + 8 * j);
+            const float4 b1 = *reinterpret_cast<const float4*>(sbias + 32 * c + 8 * j + 4);
+            float a[8] = {__uint_as_float(v[c][8 * j]) + b0.x, __uint_as_float(v[c][8 * j + 1]) + b0.y,
+                          __uint_as_float(v[c][8 * j + 2]) + b0.z, __uint_as_float(v[c][8 * j + 3]) + b0.w,
+                          __uint_as_float(v[c][8 * j + 4]) + b1.x, __uint_as_float(v[c][8 * j + 5]) + b1.y,
+                          __uint_as_float(v[c][8 * j + 6]) + b1.z, __uint_as_float(v[c][8 * j + 7]) + b1.w};
+            if (act != CFFM_ACT_NONE) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[e] = apply_act(a[e], act);
+            }
+            *reinterpret_cast<uint4*>(stg8 + lane * P16 + 64 * c + 16 * j) =
+                make_uint4(pack_half2(a[0], a[1]), pack_half2(a[2], a[3]), pack_half2(a[4], a[5]), pack_half2(a[6], a[7]));
+          }
+        }
+        __syncwarp();
+        constexpr int LPR = WCOLS / 8;                         // lanes per row (16-byte pieces): 4 or 8
+        constexpr int RPP = 32 / LPR;                          // rows per pass: 8 or 4
+        const int piece = lane % LPR, rr = lane / LPR;
+        const int col = wcol0 + 8 * piece;
+        if (col < N && !(dbg & 1)) {
+          __half* obase = ep.out16 + static_cast<int64_t>(wrow0 + rr) * ep.ldo16 + col;
+#pragma unroll
+          for (int i = 0; i < LPR; ++i) {
+            const int row = wrow0 + rr + RPP * i;
+            const uint4 val = *reinterpret_cast<const uint4*>(stg8 + (rr + RPP * i) * P16 + 16 * piece);
+            if (row < M) *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(RPP * i) * ep.ldo16) = val;
+          }
+        }
+        __syncwarp();                                          // staging buffer is re-used by the next tile
+        continue;
+      }
+      // ---- general path: fp32 and/or fp16 output, optional fp32 residual (may alias out32)
+      const int rsub = lane >> 3, csub = (lane & 7) * 4;       // after the transpose: 4 rows x 8 float4 per pass
+      float4 b4[NCH], r4[NCH][8];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col = wcol0 + 32 * c + csub;
+        b4[c] = (ep.bias != nullptr && col < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + col))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.residual != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = wrow0 + rsub + 4 * i;
+            r4[c][i] = (row < M && col < N)
+                           ? *reinterpret_cast<const float4*>(ep.residual + static_cast<int64_t>(row) * ep.ldr + col)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
       ptx::mbar_wait(&tfull_bar[acc], aph);
       ptx::tc_fence_after();
-      constexpr int NCH = BN / 64;                             // chunks per warp
       uint32_t v[NCH][32];
 #pragma unroll
       for (int c = 0; c < NCH; ++c)
-        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + (2 * c + chalf) * 32, v[c]);
+        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + ch * WCOLS + 32 * c, v[c]);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);       // registers hold the tile: MMA may reuse the stage
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (dbg & 2) continue;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        const int col = n0 + (2 * c + chalf) * 32 + csub;      // this lane's 4 columns after the transpose
+        const int col = wcol0 + 32 * c + csub;                 // this lane's 4 columns after the transpose
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -180,29 +271,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                           __uint_as_float(v[c][4 * j + 2]), __uint_as_float(v[c][4 * j + 3]));
         __syncwarp();
         if (col < N) {                                         // N % 8 == 0: the float4 is all-valid or all-invalid
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ep.bias != nullptr) b4 = *reinterpret_cast<const float4*>(ep.bias + col);
-          const int rbase = m0 + wq * 32 + rsub;
-          float4 r4[8];
-          if (ep.residual != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = rbase + 4 * i;
-              r4[i] = row < M ? *reinterpret_cast<const float4*>(ep.residual + static_cast<int64_t>(row) * ep.ldr + col)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int row = rbase + 4 * i;
+            const int row = wrow0 + rsub + 4 * i;
             float4 a = *reinterpret_cast<const float4*>(stg + (rsub + 4 * i) * STG_LD + csub);
-            a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-            if (ep.act != CFFM_ACT_NONE) {
-              a.x = apply_act(a.x, ep.act); a.y = apply_act(a.y, ep.act);
-              a.z = apply_act(a.z, ep.act); a.w = apply_act(a.w, ep.act);
+            a.x += b4[c].x; a.y += b4[c].y; a.z += b4[c].z; a.w += b4[c].w;
+            if (act != CFFM_ACT_NONE) {
+              a.x = apply_act(a.x, act); a.y = apply_act(a.y, act);
+              a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
             }
-            if (ep.residual != nullptr) { a.x += r4[i].x; a.y += r4[i].y; a.z += r4[i].z; a.w += r4[i].w; }
-            if (row < M) {
+            if (ep.residual != nullptr) { a.x += r4[c][i].x; a.y += r4[c][i].y; a.z += r4[c][i].z; a.w += r4[c][i].w; }
+            if (row < M && !(dbg & 1)) {
               if (ep.out32 != nullptr)
                 *reinterpret_cast<float4*>(ep.out32 + static_cast<int64_t>(row) * ep.ldo32 + col) = a;
               if (ep.out16 != nullptr) {
@@ -228,6 +307,7 @@ constexpr int CK_T = 64;
 __global__ void __launch_bounds__(256)
 gemm_check_kernel(const __half* __restrict__ A, int64_t lda, const __half* __restrict__ W, int64_t ldw,
                   const Epilogue ep, int M, int N, int K) {
+  pdl_sync();
   __shared__ float sA[16][CK_T + 1];
   __shared__ float sW[16][CK_T + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -311,7 +391,7 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t K, int64_
   return CFFM_OK;
 }
 
-template <int BN>
+template <int BN, bool F16_ONLY>
 int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const Epilogue& ep, int M, int N, int K,
                    cudaStream_t st) {
   CUtensorMap tmA, tmW;
@@ -322,14 +402,14 @@ int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, F16_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg<BN>::SMEM_BYTES);
   });
   CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
   const int tiles = tiles_n * tiles_m;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmW, ep, M, N, K, tiles_n, tiles);
+  launch_k(gemm_tcgen05_kernel<BN, F16_ONLY>, grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st, tmA, tmW, ep, M, N, K, tiles_n, tiles);
   return launch_status("gemm_tcgen05_kernel");
 }
 
@@ -353,14 +433,21 @@ extern "C" int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t 
                CFFM_E_BADARG, "gemm: bad output/residual stride");
   CFFM_REQUIRE(act >= CFFM_ACT_NONE && act <= CFFM_ACT_RELU, CFFM_E_BADARG, "gemm: bad act %d", act);
   Epilogue ep{bias, residual, ldr, static_cast<__half*>(out_f16), ldo16, out_f32, ldo32, act};
+  if (const char* dbg = getenv("CFFM_GEMM_DEBUG")) ep.act |= atoi(dbg) << 8;   // bring-up experiments only (tools/gemm_probe.py)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (impl == CFFM_GEMM_CHECK) {
     dim3 grid((N + CK_T - 1) / CK_T, (M + CK_T - 1) / CK_T);
-    gemm_check_kernel<<<grid, 256, 0, st>>>(static_cast<const __half*>(A), lda, static_cast<const __half*>(W), ldw, ep,
+    launch_k(gemm_check_kernel, grid, 256, 0, st, static_cast<const __half*>(A), lda, static_cast<const __half*>(W), ldw, ep,
                                             M, N, K);
     return launch_status("gemm_check_kernel");
   }
   CFFM_REQUIRE(impl == CFFM_GEMM_TCGEN05, CFFM_E_BADARG, "gemm: bad impl %d", impl);
-  if (N % 128 == 0 || (N % 64 != 0 && N > 64)) return launch_tcgen05<128>(A, lda, W, ldw, ep, M, N, K, st);
-  return launch_tcgen05<64>(A, lda, W, ldw, ep, M, N, K, st);
+  const bool f16_only = out_f16 != nullptr && out_f32 == nullptr && residual == nullptr;
+  const bool wide = N % 128 == 0 || (N % 64 != 0 && N > 64);
+  if (f16_only) {
+    return wide ? launch_tcgen05<128, true>(A, lda, W, ldw, ep, M, N, K, st)
+                : launch_tcgen05<64, true>(A, lda, W, ldw, ep, M, N, K, st);
+  }
+  return wide ? launch_tcgen05<128, false>(A, lda, W, ldw, ep, M, N, K, st)
+              : launch_tcgen05<64, false>(A, lda, W, ldw, ep, M, N, K, st);
 }
