@@ -190,10 +190,18 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
     graphed = None
-    if args.shard == "frames" and world > 1:
+    frames_mode = args.shard == "frames" and world > 1
+    if frames_mode:
+        # the global batch (B clips per GPU x world) with its FRAMES spread over the ranks; one NCCL all-gather of the
+        # reference-frame K/V per step (vss_cffm_b200/parallel.py).  Launched eagerly (the collective is not captured).
         from vss_cffm_b200 import parallel
-        runner = parallel.FrameShardedRunner(model, world, rank)
-        step_dev = lambda: runner.predict_labels(imgs_dev, metas)
+        plan = parallel.FrameShardPlan(B * world, T, world)
+        runner = parallel.FrameShardedRunner(model, plan, rank)
+        gen = lambda b, t: synth.synth_array((3, H, W), 7000 + 16 * b + t)
+        fr_host = torch.stack([gen(b, t) for b, t in runner.local_frames()]).pin_memory()
+        fr_dev = fr_host.cuda()
+        labels_host = torch.empty(len(plan.targets[rank]), H, W, dtype=torch.int64).pin_memory()
+        step_dev = lambda: runner.run(fr_dev)
         step_eager = step_dev
     else:
         step_eager = lambda: model.predict_labels(imgs_dev, metas)
@@ -205,6 +213,11 @@ def main():
             step_dev = graphed.replay
 
     def step_e2e():
+        if frames_mode:
+            fr_dev.copy_(fr_host, non_blocking=True)
+            lab = runner.run(fr_dev)
+            labels_host.copy_(lab, non_blocking=True)
+            return lab
         if graphed is not None:
             lab = graphed(imgs_host)                              # H2D of the pinned frames + graph replay
         else:

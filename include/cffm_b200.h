@@ -115,12 +115,25 @@ int cffm_head_fuse(const void* p1, const void* p2, const void* p3, const void* p
 int cffm_cffa_norm(const float* x, const float* gamma, const float* beta, float eps, void* xn,
                    void* xt_pad, int B, int T, int H, int W, int Hp, int Wp, int C, void* stream);
 
+/* Same kernel on an arbitrary list of frames (frame-sharded multi-GPU path): x fp32 [n_frames,H,W,C];
+ * frames >= first_target are target frames and are also written, zero-padded, to xt_pad
+ * [n_frames-first_target,Hp,Wp,C] (xt_pad may be NULL when first_target == n_frames). */
+int cffm_cffa_norm_frames(const float* x, const float* gamma, const float* beta, float eps, void* xn,
+                          void* xt_pad, int n_frames, int first_target, int H, int W, int Hp, int Wp,
+                          int C, void* stream);
+
 /* CFFA step 2: coarse-to-fine pooling of the (virtually zero-padded) LN'ed frames.
  * xn fp16 [T,B,H,W,C] frame-major.  pooled fp16 [B, P, C], P = nW*(1+1+4+9): target 7x7 fc-pool | ref0 7x7 | ref1 bilinear
  * (Hp->6*nWh) + 3x3 | ref2 bilinear + 2x2, each map row-major.  pool_w fp32 packed
  * [49+49+9+4], pool_b fp32 [4].  cffm_transformer.py:739-805. */
 int cffm_cffa_pool(const void* xn, int B, int T, int H, int W, int C, const float* pool_w,
                    const float* pool_b, void* pooled, void* stream);
+
+/* One pooling level of n independent LN'ed frames xn fp16 [n,H,W,C] (frame-sharded multi-GPU path: the
+ * owner of a reference frame pools it for its temporal role).  level 0: target 7x7 | 1: ref0 7x7 |
+ * 2: ref1 bilinear + 3x3 | 3: ref2 bilinear + 2x2; pooled fp16 [n, {1,1,4,9}[level]*nW, C]. */
+int cffm_cffa_pool_level(const void* xn, int n_frames, int level, int H, int W, int C,
+                         const float* pool_w, const float* pool_b, void* pooled, void* stream);
 
 /* Cross-frame feature mining attention with in-kernel K/V assembling (no roll / partition /
  * unfold / cat is materialised).  qkv_t fp16 [B, Hp*Wp, 3C] = qkv(xt_pad); kv_pooled fp16

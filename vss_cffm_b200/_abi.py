@@ -35,7 +35,9 @@ SIGNATURES = {
     "cffm_head_fuse": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, vp,
                         i64, vp], i32),
     "cffm_cffa_norm": ([vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp], i32),
+    "cffm_cffa_norm_frames": ([vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp], i32),
     "cffm_cffa_pool": ([vp, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
+    "cffm_cffa_pool_level": ([vp, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
     "cffm_cfm_attention": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),
     "cffm_cfm_key_sources": ([i32, i32, vp, vp], i32),
     "cffm_resize_nhwc_to_nchw": ([vp, i32, i64, vp, i32, i32, i32, i32, i32, i32, vp], i32),

@@ -319,13 +319,13 @@ head_fuse_kernel(const __half* __restrict__ p1, const __half* __restrict__ p2, c
 // CFFA norm: LN over C = 256 of every frame; one warp per token, 8 channels per lane.
 __global__ void __launch_bounds__(256)
 cffa_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 float eps, __half* __restrict__ xn, __half* __restrict__ xt_pad, int B, int T, int H, int W, int Hp,
-                 int Wp) {
+                 float eps, __half* __restrict__ xn, __half* __restrict__ xt_pad, int n_frames, int first_target, int H,
+                 int W, int Hp, int Wp) {
   pdl_sync();
   constexpr int C = 256;
   const int64_t tok = blockIdx.x * 8ll + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (tok >= static_cast<int64_t>(B) * T * H * W) return;
+  if (tok >= static_cast<int64_t>(n_frames) * H * W) return;
   const float* px = x + tok * C + lane * 8;
   const float4 a = *reinterpret_cast<const float4*>(px), b = *reinterpret_cast<const float4*>(px + 4);
   float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -347,30 +347,39 @@ cffa_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   *reinterpret_cast<half8*>(xn + tok * C + lane * 8) = o;
   const int xx = static_cast<int>(tok % W), yy = static_cast<int>((tok / W) % H);
   const int frame = static_cast<int>(tok / (static_cast<int64_t>(W) * H));   // frame-major: frame = t*B + b
-  const int bi = frame - (T - 1) * B;
-  if (bi >= 0)
+  const int bi = frame - first_target;                          // frames >= first_target are target frames
+  if (bi >= 0 && xt_pad != nullptr)
     *reinterpret_cast<half8*>(xt_pad + ((static_cast<int64_t>(bi) * Hp + yy) * Wp + xx) * C + lane * 8) = o;
 }
 
 // CFFA pooling: one warp per pooled token. Levels: 0 target 7x7 | 1 ref0 7x7 | 2 ref1 resize+3x3 | 3 ref2 resize+2x2
 __global__ void __launch_bounds__(256)
 cffa_pool_kernel(const __half* __restrict__ xn, int B, int T, int H, int W, int Hp, int Wp,
-                 const float* __restrict__ pool_w, const float* __restrict__ pool_b, __half* __restrict__ pooled) {
+                 const float* __restrict__ pool_w, const float* __restrict__ pool_b, __half* __restrict__ pooled,
+                 int only_level) {
   pdl_sync();
   constexpr int C = 256, WS = 7;
-  const int nWh = Hp / WS, nWw = Wp / WS, nW = nWh * nWw, P = 15 * nW;
+  const int nWh = Hp / WS, nWw = Wp / WS, nW = nWh * nWw;
+  // only_level < 0: all four levels of B clips from the frame-major stack xn [T,B,H,W,C] (P = 15 nW tokens per clip);
+  // only_level = l: level l of B independent frames xn [B,H,W,C] (P = {1,1,4,9}[l] nW tokens per frame)
+  const int P = only_level < 0 ? 15 * nW : (only_level < 2 ? nW : (only_level == 2 ? 4 * nW : 9 * nW));
   const int64_t gw = blockIdx.x * 8ll + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (gw >= static_cast<int64_t>(B) * P) return;
   const int b = static_cast<int>(gw / P);
   int pos = static_cast<int>(gw % P);
   int level, frame, wg, gwid, woff;
-  if (pos < nW) { level = 0; frame = T - 1; wg = 7; gwid = nWw; woff = 0; }
-  else if (pos < 2 * nW) { level = 1; pos -= nW; frame = 0; wg = 7; gwid = nWw; woff = 49; }
-  else if (pos < 6 * nW) { level = 2; pos -= 2 * nW; frame = 1; wg = 3; gwid = 2 * nWw; woff = 98; }
-  else { level = 3; pos -= 6 * nW; frame = 2; wg = 2; gwid = 3 * nWw; woff = 107; }
+  if (only_level >= 0) level = only_level;
+  else if (pos < nW) level = 0;
+  else if (pos < 2 * nW) { level = 1; pos -= nW; }
+  else if (pos < 6 * nW) { level = 2; pos -= 2 * nW; }
+  else { level = 3; pos -= 6 * nW; }
+  if (level == 0) { frame = T - 1; wg = 7; gwid = nWw; woff = 0; }
+  else if (level == 1) { frame = 0; wg = 7; gwid = nWw; woff = 49; }
+  else if (level == 2) { frame = 1; wg = 3; gwid = 2 * nWw; woff = 98; }
+  else { frame = 2; wg = 2; gwid = 3 * nWw; woff = 107; }
   const int py = pos / gwid, px = pos % gwid;
-  const __half* src = xn + (static_cast<int64_t>(frame) * B + b) * H * W * C + lane * 8;
+  const __half* src = xn + (only_level < 0 ? static_cast<int64_t>(frame) * B + b : static_cast<int64_t>(b)) * H * W * C + lane * 8;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -665,7 +674,21 @@ extern "C" int cffm_cffa_norm(const float* x, const float* gamma, const float* b
   CFFM_REQUIRE(C == 256, CFFM_E_UNSUPPORTED, "cffa_norm: built for C=256, got %d", C);
   const int64_t tokens = static_cast<int64_t>(B) * T * H * W;
   launch_k(cffa_norm_kernel, static_cast<int>((tokens + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
-      x, gamma, beta, eps, static_cast<__half*>(xn), static_cast<__half*>(xt_pad), B, T, H, W, Hp, Wp);
+      x, gamma, beta, eps, static_cast<__half*>(xn), static_cast<__half*>(xt_pad), B * T, (T - 1) * B, H, W, Hp, Wp);
+  return launch_status("cffa_norm_kernel");
+}
+
+extern "C" int cffm_cffa_norm_frames(const float* x, const float* gamma, const float* beta, float eps, void* xn,
+                                     void* xt_pad, int n_frames, int first_target, int H, int W, int Hp, int Wp, int C,
+                                     void* stream) {
+  CFFM_REQUIRE(x && gamma && beta && xn, CFFM_E_BADARG, "cffa_norm_frames: null pointer");
+  CFFM_REQUIRE(n_frames > 0 && first_target >= 0 && first_target <= n_frames && H > 0 && W > 0 && Hp >= H && Wp >= W,
+               CFFM_E_BADARG, "cffa_norm_frames: bad size");
+  CFFM_REQUIRE(first_target == n_frames || xt_pad, CFFM_E_BADARG, "cffa_norm_frames: xt_pad required when targets exist");
+  CFFM_REQUIRE(C == 256, CFFM_E_UNSUPPORTED, "cffa_norm_frames: built for C=256, got %d", C);
+  const int64_t tokens = static_cast<int64_t>(n_frames) * H * W;
+  launch_k(cffa_norm_kernel, static_cast<int>((tokens + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), x, gamma,
+           beta, eps, static_cast<__half*>(xn), static_cast<__half*>(xt_pad), n_frames, first_target, H, W, Hp, Wp);
   return launch_status("cffa_norm_kernel");
 }
 
@@ -678,7 +701,20 @@ extern "C" int cffm_cffa_pool(const void* xn, int B, int T, int H, int W, int C,
   const int Hp = (H + 6) / 7 * 7, Wp = (W + 6) / 7 * 7;
   const int64_t warps = static_cast<int64_t>(B) * 15 * (Hp / 7) * (Wp / 7);
   launch_k(cffa_pool_kernel, static_cast<int>((warps + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
-      static_cast<const __half*>(xn), B, T, H, W, Hp, Wp, pool_w, pool_b, static_cast<__half*>(pooled));
+      static_cast<const __half*>(xn), B, T, H, W, Hp, Wp, pool_w, pool_b, static_cast<__half*>(pooled), -1);
+  return launch_status("cffa_pool_kernel");
+}
+
+extern "C" int cffm_cffa_pool_level(const void* xn, int n_frames, int level, int H, int W, int C, const float* pool_w,
+                                    const float* pool_b, void* pooled, void* stream) {
+  CFFM_REQUIRE(xn && pool_w && pool_b && pooled, CFFM_E_BADARG, "cffa_pool_level: null pointer");
+  CFFM_REQUIRE(n_frames > 0 && H > 0 && W > 0 && level >= 0 && level <= 3, CFFM_E_BADARG, "cffa_pool_level: bad size/level");
+  CFFM_REQUIRE(C == 256, CFFM_E_UNSUPPORTED, "cffa_pool_level: built for C=256, got %d", C);
+  const int Hp = (H + 6) / 7 * 7, Wp = (W + 6) / 7 * 7;
+  const int per = level < 2 ? 1 : (level == 2 ? 4 : 9);
+  const int64_t warps = static_cast<int64_t>(n_frames) * per * (Hp / 7) * (Wp / 7);
+  launch_k(cffa_pool_kernel, static_cast<int>((warps + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream),
+           static_cast<const __half*>(xn), n_frames, 4, H, W, Hp, Wp, pool_w, pool_b, static_cast<__half*>(pooled), level);
   return launch_status("cffa_pool_kernel");
 }
 

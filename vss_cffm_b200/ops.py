@@ -127,6 +127,22 @@ def cffa_pool(xn, B, T, H, W, C, pool_w, pool_b, pooled):
     _abi.call("cffm_cffa_pool", _ptr(xn), B, T, H, W, C, _ptr(pool_w), _ptr(pool_b), _ptr(pooled), _stream())
 
 
+def cffa_norm_frames(x, gamma, beta, eps, xn, xt_pad, n_frames, first_target, H, W, Hp, Wp, C):
+    _chk(x, _F, "cffa_norm_frames.x"); _chk(xn, _H, "cffa_norm_frames.xn")
+    assert x.is_contiguous() and xn.is_contiguous() and x.numel() == n_frames * H * W * C == xn.numel()
+    if xt_pad is not None:
+        _chk(xt_pad, _H, "cffa_norm_frames.xt_pad")
+        assert xt_pad.is_contiguous() and xt_pad.numel() == (n_frames - first_target) * Hp * Wp * C
+    _abi.call("cffm_cffa_norm_frames", _ptr(x), _ptr(gamma), _ptr(beta), float(eps), _ptr(xn), _ptr(xt_pad), n_frames,
+              first_target, H, W, Hp, Wp, C, _stream())
+
+
+def cffa_pool_level(xn, n_frames, level, H, W, C, pool_w, pool_b, pooled):
+    _chk(xn, _H, "cffa_pool_level.xn"); _chk(pooled, _H, "cffa_pool_level.pooled")
+    assert xn.is_contiguous() and pooled.is_contiguous() and xn.numel() == n_frames * H * W * C
+    _abi.call("cffm_cffa_pool_level", _ptr(xn), n_frames, level, H, W, C, _ptr(pool_w), _ptr(pool_b), _ptr(pooled), _stream())
+
+
 def cfm_attention(qkv_t, kv_pooled, bias, out, B, H, W, C, heads, scale):
     _chk(qkv_t, _H, "cfm.qkv_t"); _chk(kv_pooled, _H, "cfm.kv_pooled"); _chk(bias, _F, "cfm.bias"); _chk(out, _H, "cfm.out")
     assert qkv_t.is_contiguous() and kv_pooled.is_contiguous() and bias.is_contiguous() and out.is_contiguous()

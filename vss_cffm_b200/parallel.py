@@ -1,0 +1,186 @@
+"""Multi-GPU execution of the CFFM hot path (one process per GPU, torch.distributed / NCCL over NVLink).
+
+Two ways the path shards:
+
+1. **Clips** are independent in eval mode (BatchNorm uses running statistics, nothing mixes clips): shard the clip
+   batch across ranks, no data-path collective.  This is the reference's own strategy (DistributedSampler + DDP,
+   tools/test.py:123-149) and what ``bench.py --gpus N`` measures by default (``shard_clips``).
+
+2. **Frames**: backbone + MLP decoder are per frame; only the CFFM blocks mix the frames of a clip, and only by
+   reading, for every block, the pooled K/V of the three reference frames (cffm_transformer.py:780-805, :470-518).
+   Reference frames are never modified by a block (:826), so the owner of reference frame (b, t) can compute
+   LN -> role-t pooling -> K/V projection for ALL blocks up front.  ``FrameShardedRunner`` does exactly that, then
+   issues ONE all-gather of the packed per-frame K/V ([depth, 729, 512] fp16 per reference frame, 81/324/729 tokens
+   used for role 0/1/2) and the owners of the target frames run the CFM attention + FFN locally.
+   The payload is ~1.5 MB per reference frame: latency-bound on NVLink, so it is a single NCCL call, not a fused
+   kernel (there is no compute to overlap it with on the target-owner's critical path except its own QKV GEMM).
+
+Ownership: frame (b, t) of a global batch of Bg clips lives on rank (b + t) mod G when Bg >= G (every rank then owns
+Bg/G frames of each temporal role, i.e. Bg/G targets: balanced) and on rank (b*T + t) mod G otherwise.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _abi, ops
+from .workspace import Workspace
+
+_H, _F = torch.float16, torch.float32
+ROLE_TOKENS = (1, 4, 9)                                     # pooled tokens per window for reference role 0, 1, 2
+
+
+def shard_clips(n_clips, world, rank):
+    """Contiguous clip range of ``rank`` (clip sharding, no collective)."""
+    per, rem = divmod(n_clips, world)
+    lo = rank * per + min(rank, rem)
+    return range(lo, lo + per + (1 if rank < rem else 0))
+
+
+class FrameShardPlan:
+    """Static ownership map of the frames of a global batch: pure host logic (tested on CPU with gloo)."""
+
+    def __init__(self, n_clips, n_frames, world):
+        if n_frames != 4:
+            raise _abi.CffmError("CFFM needs exactly 3 reference frames + 1 target per clip (cffm_head.py:93-94)")
+        self.Bg, self.T, self.G = n_clips, n_frames, world
+        self.frames = [[] for _ in range(world)]            # rank -> [(b, t)] frame-major (sorted by t, then b)
+        for t in range(n_frames):
+            for b in range(n_clips):
+                self.frames[self.owner(b, t)].append((b, t))
+        self.refs = [[f for f in fr if f[1] < n_frames - 1] for fr in self.frames]
+        self.targets = [[b for b, t in fr if t == n_frames - 1] for fr in self.frames]
+        self.max_slots = max(1, max(len(r) for r in self.refs))
+        self._slot = {f: (rank, i) for rank, r in enumerate(self.refs) for i, f in enumerate(r)}
+
+    def owner(self, b, t):
+        return (b + t) % self.G if self.Bg >= self.G else (b * self.T + t) % self.G
+
+    def slot_of(self, b, t):
+        """(owner rank, slot index in that rank's send buffer) of reference frame (b, t)."""
+        return self._slot[(b, t)]
+
+    def gathered_index(self, b, t):
+        """Row of reference frame (b, t) in the all-gathered buffer [G * max_slots, ...]."""
+        rank, slot = self._slot[(b, t)]
+        return rank * self.max_slots + slot
+
+
+def all_gather_slots(send, group=None):
+    """One all-gather of every rank's [max_slots, ...] buffer -> [G * max_slots, ...] (NCCL on GPUs, gloo in tests)."""
+    world = dist.get_world_size(group)
+    recv = send.new_empty((world * send.shape[0],) + tuple(send.shape[1:]))
+    if dist.get_backend(group) == "gloo":
+        dist.all_gather(list(recv.chunk(world, dim=0)), send, group=group)
+    else:
+        dist.all_gather_into_tensor(recv, send, group=group)
+    return recv
+
+
+def assemble_kv(plan, gathered, clip, block, nW, out):
+    """Copy the K/V of clip ``clip``'s three reference frames for ``block`` from the gathered buffer
+    [G*max_slots, depth, 9 nW, 2C] into ``out`` [15 nW, 2C] behind the nW pooled-target rows (layout of
+    cffm_cfm_attention's kv_pooled: target | ref0 | ref1 | ref2)."""
+    off = nW
+    for t, per in enumerate(ROLE_TOKENS):
+        n = per * nW
+        out[off:off + n].copy_(gathered[plan.gathered_index(clip, t), block, :n])
+        off += n
+    return out
+
+
+class FrameShardedRunner:
+    """Runs EncoderDecoder_clips inference with the frames of a global clip batch sharded over the ranks."""
+
+    def __init__(self, model, plan, rank, group=None):
+        self.model, self.plan, self.rank, self.group = model, plan, rank, group
+        self.ws = Workspace()
+
+    def local_frames(self):
+        """[(clip, t)] this rank must be fed, in the order ``run`` expects them."""
+        return list(self.plan.frames[self.rank])
+
+    def run(self, frames):
+        """frames: (n_local, 3, H, W) fp32 on this rank's device, ordered as ``local_frames()``.
+        Returns int64 labels (n_targets, H, W) for the clips ``plan.targets[rank]`` (may be empty)."""
+        model, plan, ws = self.model, self.plan, self.ws
+        head = model.decode_head
+        P = head._plan or head._build_plan()
+        E, HEADS = head.embed_dim, 8
+        mine = plan.frames[self.rank]
+        n_loc, n_ref, n_t = len(mine), len(plan.refs[self.rank]), len(plan.targets[self.rank])
+        assert frames.shape[0] == n_loc
+        H, W = frames.shape[-2:]
+        dev = frames.device
+        depth = len(P["blocks"])
+        # ---- per-frame work: backbone + folded MLP decoder (cffm_head.py:102-133)
+        if n_loc:
+            feats = [head._as_nhwc16(t) for t in model.extract_feat(frames)]
+            sizes = [(t.shape[1], t.shape[2]) for t in feats]
+            h, w = sizes[0]
+            proj = []
+            for i, t in enumerate(feats):
+                p = ws.get(f"p{i}", (n_loc * sizes[i][0] * sizes[i][1], E), _H, device=dev)
+                ops.gemm(t.reshape(-1, t.shape[3]), P["pw"][i], out16=p)
+                proj.append(p)
+        else:
+            h, w = H // 4, W // 4
+        h2, w2 = h // 2, w // 2
+        HW = h2 * w2
+        Hp, Wp = (h2 + 6) // 7 * 7, (w2 + 6) // 7 * 7
+        nW = (Hp // 7) * (Wp // 7)
+        x32 = ws.get("x32", (max(n_loc, 1) * HW, E), _F, device=dev)
+        c16 = ws.get("c16", (max(n_loc, 1) * HW, E), _H, device=dev)
+        if n_loc:
+            ops.head_fuse(proj, sizes, n_loc, E, 0, P["shift"], half32=x32, half16=c16)
+        # ---- reference frames: K/V of every block, packed for the exchange (cffm_transformer.py:780-805, :495-518)
+        send = ws.get("send", (plan.max_slots, depth, 9 * nW, 2 * E), _H, device=dev, zero=True)
+        if n_ref:
+            xn = ws.get("xn_ref", (n_ref * HW, E), _H, device=dev)
+            for i, b in enumerate(P["blocks"]):
+                ops.cffa_norm_frames(x32[:n_ref * HW], b["n1g"], b["n1b"], b["n1eps"], xn, None, n_ref, n_ref, h2, w2, Hp, Wp, E)
+                for slot, (_, t) in enumerate(plan.refs[self.rank]):
+                    n = ROLE_TOKENS[t] * nW
+                    pooled = ws.get(f"pooled_r{t}", (n, E), _H, device=dev)
+                    ops.cffa_pool_level(xn[slot * HW:(slot + 1) * HW], 1, t + 1, h2, w2, E, b["pool_w"], b["pool_b"], pooled)
+                    ops.gemm(pooled, b["qkv_w"][E:], bias=b["qkv_b"][E:], out16=send[slot, i, :n])
+        # ---- the one collective of the path
+        gathered = all_gather_slots(send, self.group) if plan.G > 1 else send
+        if not n_t:
+            return torch.empty(0, H, W, dtype=torch.int64, device=dev)
+        # ---- target frames: CFFM blocks (cffm_transformer.py:709-832) with the gathered reference K/V
+        xt = x32[n_ref * HW:(n_ref + n_t) * HW]
+        ct16 = c16[n_ref * HW:(n_ref + n_t) * HW]
+        xn_t = ws.get("xn_t", (n_t * HW, E), _H, device=dev)
+        xt_pad = ws.get("xt_pad", (n_t * Hp * Wp, E), _H, device=dev, zero=True)
+        pooled_t = ws.get("pooled_t", (n_t * nW, E), _H, device=dev)
+        kv_t = ws.get("kv_t", (n_t * nW, 2 * E), _H, device=dev)
+        qkv_t = ws.get("qkv_t", (n_t * Hp * Wp, 3 * E), _H, device=dev)
+        kvp = ws.get("kvp", (n_t, 15 * nW, 2 * E), _H, device=dev)
+        ao = ws.get("ao", (n_t * HW, E), _H, device=dev)
+        xn2 = ws.get("xn2", (n_t * HW, E), _H, device=dev)
+        hid = ws.get("hid", (n_t * HW, 4 * E), _H, device=dev)
+        xt16 = ws.get("xt16", (n_t * HW, E), _H, device=dev)
+        for i, b in enumerate(P["blocks"]):
+            ops.cffa_norm_frames(xt, b["n1g"], b["n1b"], b["n1eps"], xn_t, xt_pad, n_t, 0, h2, w2, Hp, Wp, E)
+            ops.cffa_pool_level(xn_t, n_t, 0, h2, w2, E, b["pool_w"], b["pool_b"], pooled_t)
+            ops.gemm(xt_pad, b["qkv_w"], bias=b["qkv_b"], out16=qkv_t)
+            ops.gemm(pooled_t, b["qkv_w"][E:], bias=b["qkv_b"][E:], out16=kv_t)
+            kvp[:, :nW].copy_(kv_t.view(n_t, nW, 2 * E))
+            for j, clip in enumerate(plan.targets[self.rank]):
+                assemble_kv(plan, gathered, clip, i, nW, kvp[j])
+            ops.cfm_attention(qkv_t, kvp.view(n_t * 15 * nW, 2 * E), b["bias"], ao, n_t, h2, w2, E, HEADS, (E // HEADS) ** -0.5)
+            ops.gemm(ao, b["proj_w"], bias=b["proj_b"], residual=xt, out32=xt)
+            ops.layernorm(xt, b["n2g"], b["n2b"], b["n2eps"], out16=xn2)
+            ops.gemm(xn2, b["f1w"], bias=b["f1b"], out16=hid, act=ops.ACT_GELU)
+            ops.gemm(hid, b["f2w"], bias=b["f2b"], residual=xt, out32=xt, out16=xt16 if i == depth - 1 else None)
+        # ---- classifier + fused x2 / x4 resize + argmax (cffm_head.py:145-149, encoder_decoder.py:373-377,564)
+        lg = ws.get("lg", (n_t * HW, P["ncp"]), _F, device=dev)
+        ops.gemm(ct16, P["pred2_w"][:, :E], bias=P["pred2_b"], out32=lg)
+        ops.gemm(xt16, P["pred2_w"][:, E:], residual=lg, out32=lg)
+        labels = torch.empty(n_t, H, W, dtype=torch.int64, device=dev)
+        if ops.upsample2_argmax_supported(h, w, H, W):
+            ops.upsample2_argmax(lg, model.num_classes, labels, n_t, h2, w2, h, w, H, W)
+        else:
+            logits = torch.empty(n_t, model.num_classes, h, w, dtype=_F, device=dev)
+            ops.resize_nhwc_to_nchw(lg, model.num_classes, logits, n_t, h2, w2, h, w)
+            ops.resize_argmax(logits, labels, n_t, model.num_classes, h, w, H, W)
+        return labels
