@@ -374,11 +374,12 @@ class CFFMHead_clips_resize1_8(BaseDecodeHead_clips_flow):
         h, w = sizes[0]
         t_perm = 0 if (frame_major or T == 1) else T
         # ---- per-frame MLP decoder, folded (:108-119)
-        proj = []
-        for i, t in enumerate(feats):
-            p = ws.get(f"p{i}", (N * sizes[i][0] * sizes[i][1], E), _H)
-            ops.gemm(t.reshape(-1, t.shape[3]), P["pw"][i], out16=p)
-            proj.append(p)
+        proj = [ws.get(f"p{i}", (N * sizes[i][0] * sizes[i][1], E), _H) for i in range(4)]
+        with ops.fork():                                         # the three small projections beside the big one
+            for i in (1, 2, 3):
+                ops.gemm(feats[i].reshape(-1, feats[i].shape[3]), P["pw"][i], out16=proj[i])
+        ops.gemm(feats[0].reshape(-1, feats[0].shape[3]), P["pw"][0], out16=proj[0])
+        ops.join()
         early = num_clips != self.num_clips                      # eval-mode early return (:127-129)
         if early:
             c_full = ws.get("c_full", (N * h * w, E), _H)
@@ -419,9 +420,11 @@ class CFFMHead_clips_resize1_8(BaseDecodeHead_clips_flow):
         xt16 = ws.get("xt16", (B * HW, E), _H)
         for i, b in enumerate(P["blocks"]):
             ops.cffa_norm(x32, b["n1g"], b["n1b"], b["n1eps"], xn, xt_pad, B, T, h2, w2, Hp, Wp, E)
-            ops.cffa_pool(xn, B, T, h2, w2, E, b["pool_w"], b["pool_b"], pooled)
+            with ops.fork():                                     # pooling + its K/V projection beside the target QKV
+                ops.cffa_pool(xn, B, T, h2, w2, E, b["pool_w"], b["pool_b"], pooled)
+                ops.gemm(pooled, b["qkv_w"][E:], bias=b["qkv_b"][E:], out16=kvp)   # Q third is dead work (:449)
             ops.gemm(xt_pad, b["qkv_w"], bias=b["qkv_b"], out16=qkv_t)
-            ops.gemm(pooled, b["qkv_w"][E:], bias=b["qkv_b"][E:], out16=kvp)       # Q third is dead work (:449)
+            ops.join()
             ops.cfm_attention(qkv_t, kvp, b["bias"], ao, B, h2, w2, E, HEADS_N, (E // HEADS_N) ** -0.5)
             ops.gemm(ao, b["proj_w"], bias=b["proj_b"], residual=xt, out32=xt)
             ops.layernorm(xt, b["n2g"], b["n2b"], b["n2eps"], out16=xn2)

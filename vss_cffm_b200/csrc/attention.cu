@@ -224,11 +224,11 @@ cfm_attention_kernel(const __half* __restrict__ qkv_t, const __half* __restrict_
   const __half* tq = qkv_t + static_cast<int64_t>(b) * Hp * Wp * (3 * C);
   const __half* pk = kv_pooled + static_cast<int64_t>(b) * P * (2 * C);
 
-  // ---- gather the assembled K/V sequence of this window/head
-  for (int i = tid; i < NKEYS_PAD * 4; i += 128) {
-    const int n = i >> 2, ch = i & 3;
-    __half* dk = Ks + n * LD + ch * 8;
-    __half* dv = Vs + n * LD + ch * 8;
+  // ---- gather the assembled K/V sequence of this window/head: one key (2 x 64 bytes) per thread per pass,
+  // its source coordinate evaluated once
+  for (int n = tid; n < NKEYS_PAD; n += 128) {
+    __half* dk = Ks + n * LD;
+    __half* dv = Vs + n * LD;
     bool valid = false;
     if (n < NKEYS) {
       const KeySrc s = cfm_key_source(n, wi, wj, nWh, nWw, Hp, Wp);
@@ -236,23 +236,29 @@ cfm_attention_kernel(const __half* __restrict__ qkv_t, const __half* __restrict_
         valid = true;
         const __half *ksrc, *vsrc;
         if (s.level == 0) {
-          const __half* row = tq + static_cast<int64_t>(s.y * Wp + s.x) * (3 * C) + h * D + ch * 8;
+          const __half* row = tq + static_cast<int64_t>(s.y * Wp + s.x) * (3 * C) + h * D;
           ksrc = row + C; vsrc = row + 2 * C;
         } else {
           const int lw = s.level <= 2 ? nWw : (s.level == 3 ? 2 * nWw : 3 * nWw);
           const int base = s.level == 1 ? 0 : (s.level == 2 ? nW : (s.level == 3 ? 2 * nW : 6 * nW));
-          const __half* row = pk + static_cast<int64_t>(base + s.y * lw + s.x) * (2 * C) + h * D + ch * 8;
+          const __half* row = pk + static_cast<int64_t>(base + s.y * lw + s.x) * (2 * C) + h * D;
           ksrc = row; vsrc = row + C;
         }
-        ptx::cp_async16(dk, ksrc);
-        ptx::cp_async16(dv, vsrc);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          ptx::cp_async16(dk + ch * 8, ksrc + ch * 8);
+          ptx::cp_async16(dv + ch * 8, vsrc + ch * 8);
+        }
       }
     }
     if (!valid) {
-      *reinterpret_cast<uint4*>(dk) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(dv) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        *reinterpret_cast<uint4*>(dk + ch * 8) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dv + ch * 8) = make_uint4(0, 0, 0, 0);
+      }
     }
-    if (ch == 0) madd[n] = n >= NKEYS ? -INFINITY : (valid ? 0.f : -100.f * LOG2E);   // -100, not -inf (:445,:490)
+    madd[n] = n >= NKEYS ? -INFINITY : (valid ? 0.f : -100.f * LOG2E);   // -100, not -inf (:445,:490)
   }
   ptx::cp_async_commit();
 

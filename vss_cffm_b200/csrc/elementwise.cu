@@ -258,60 +258,60 @@ __device__ __forceinline__ void add_bilerp(float* acc, const __half* __restrict_
   for (int e = 0; e < 8; ++e) acc[e] = fmaf(ly.w1 * lx.w1, t[e], acc[e]);
 }
 
+// One warp = one 2x2 block of full-resolution pixels x 64 channels: lane = q*8 + cc, q = pixel of the block,
+// cc = 8-channel chunk.  Every lane evaluates ONE pixel (1 + 3x4 16-byte loads, ~50 registers -> high
+// occupancy); the 2x2 mean (= resize(_c, 1/2)) is two xor-shuffles; the q = 0 lanes write the half-res outputs.
 __global__ void __launch_bounds__(256)
 head_fuse_kernel(const __half* __restrict__ p1, const __half* __restrict__ p2, const __half* __restrict__ p3,
                  const __half* __restrict__ p4, int N, int H1, int W1, int H2, int W2, int H3, int W3, int H4, int W4,
                  int C, int Tperm, const float* __restrict__ shift, __half* __restrict__ c_full,
                  float* __restrict__ h32, int64_t ldh32, __half* __restrict__ h16, int64_t ldh16) {
   pdl_sync();
-  const int chunks = C / 8, Hh = H1 / 2, Wh = W1 / 2;
-  const int64_t total = static_cast<int64_t>(N) * Hh * Wh * chunks;
+  const int groups = C / 64, Hh = H1 / 2, Wh = W1 / 2;
+  const int64_t total_warps = static_cast<int64_t>(N) * Hh * Wh * groups;
   const float sy2 = static_cast<float>(H2) / H1, sx2 = static_cast<float>(W2) / W1;
   const float sy3 = static_cast<float>(H3) / H1, sx3 = static_cast<float>(W3) / W1;
   const float sy4 = static_cast<float>(H4) / H1, sx4 = static_cast<float>(W4) / W1;
-  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
-    const int c = static_cast<int>(i % chunks) * 8;
-    const int64_t p = i / chunks;
+  const int lane = threadIdx.x & 31, q = lane >> 3, cc = lane & 7;
+  const int64_t warp0 = (blockIdx.x * 256ll + threadIdx.x) >> 5, nwarps = (gridDim.x * 256ll) >> 5;
+  for (int64_t wi = warp0; wi < total_warps; wi += nwarps) {
+    const int g = static_cast<int>(wi % groups);
+    const int64_t p = wi / groups;
     const int xh = static_cast<int>(p % Wh), yh = static_cast<int>((p / Wh) % Hh), n = static_cast<int>(p / (Wh * Hh));
     // input frame n = b*T + t (reference order) -> output slot t*B + b (frame-major, targets last)
     const int no = Tperm > 1 ? (n % Tperm) * (N / Tperm) + n / Tperm : n;
-    const int64_t po = (static_cast<int64_t>(no) * Hh + yh) * Wh + xh;
-    float sh[8], mean[8];
+    const int c = g * 64 + cc * 8;
+    const int y = 2 * yh + (q >> 1), x = 2 * xh + (q & 1);
+    float acc[8];
+    unpack8(*reinterpret_cast<const half8*>(p1 + ((static_cast<int64_t>(n) * H1 + y) * W1 + x) * C + c), acc);
     {
       const float4 s0 = *reinterpret_cast<const float4*>(shift + c), s1 = *reinterpret_cast<const float4*>(shift + c + 4);
-      sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
+      acc[0] += s0.x; acc[1] += s0.y; acc[2] += s0.z; acc[3] += s0.w;
+      acc[4] += s1.x; acc[5] += s1.y; acc[6] += s1.z; acc[7] += s1.w;
     }
+    add_bilerp(acc, p2, n, H2, W2, C, c, lerp_coord(y, sy2, H2), lerp_coord(x, sx2, W2));
+    add_bilerp(acc, p3, n, H3, W3, C, c, lerp_coord(y, sy3, H3), lerp_coord(x, sx3, W3));
+    add_bilerp(acc, p4, n, H4, W4, C, c, lerp_coord(y, sy4, H4), lerp_coord(x, sx4, W4));
 #pragma unroll
-    for (int e = 0; e < 8; ++e) mean[e] = 0.f;
+    for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.f);
+    if (c_full) *reinterpret_cast<half8*>(c_full + ((static_cast<int64_t>(no) * H1 + y) * W1 + x) * C + c) = pack8(acc);
+    // 2x2 mean in the order the scalar kernel used: ((p00 + p01) + p10) + p11 is not needed bit-for-bit;
+    // pairwise (p00 + p01) + (p10 + p11) via xor-shuffles over the two q bits
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const int y = 2 * yh + dy;
-      const Lerp ly2 = lerp_coord(y, sy2, H2), ly3 = lerp_coord(y, sy3, H3), ly4 = lerp_coord(y, sy4, H4);
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int x = 2 * xh + dx;
-        float acc[8];
-        const int64_t pix = (static_cast<int64_t>(n) * H1 + y) * W1 + x;
-        unpack8(*reinterpret_cast<const half8*>(p1 + pix * C + c), acc);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += sh[e];
-        add_bilerp(acc, p2, n, H2, W2, C, c, ly2, lerp_coord(x, sx2, W2));
-        add_bilerp(acc, p3, n, H3, W3, C, c, ly3, lerp_coord(x, sx3, W3));
-        add_bilerp(acc, p4, n, H4, W4, C, c, ly4, lerp_coord(x, sx4, W4));
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { acc[e] = fmaxf(acc[e], 0.f); mean[e] += acc[e]; }
-        if (c_full)
-          *reinterpret_cast<half8*>(c_full + ((static_cast<int64_t>(no) * H1 + y) * W1 + x) * C + c) = pack8(acc);
+    for (int e = 0; e < 8; ++e) {
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+      acc[e] *= 0.25f;
+    }
+    if (q == 0) {
+      const int64_t po = (static_cast<int64_t>(no) * Hh + yh) * Wh + xh;
+      if (h32) {
+        float* o = h32 + po * ldh32 + c;
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
       }
+      if (h16) *reinterpret_cast<half8*>(h16 + po * ldh16 + c) = pack8(acc);
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) mean[e] *= 0.25f;
-    if (h32) {
-      float* o = h32 + po * ldh32 + c;
-      *reinterpret_cast<float4*>(o) = make_float4(mean[0], mean[1], mean[2], mean[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(mean[4], mean[5], mean[6], mean[7]);
-    }
-    if (h16) *reinterpret_cast<half8*>(h16 + po * ldh16 + c) = pack8(mean);
   }
 }
 
@@ -657,10 +657,10 @@ extern "C" int cffm_head_fuse(const void* p1, const void* p2, const void* p3, co
   CFFM_REQUIRE(c_full || c_half_f32 || c_half_f16, CFFM_E_BADARG, "head_fuse: no output requested");
   CFFM_REQUIRE(N > 0 && H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && H3 > 0 && W3 > 0 && H4 > 0 && W4 > 0, CFFM_E_BADARG,
                "head_fuse: non-positive size");
-  CFFM_REQUIRE(C % 8 == 0 && H1 % 2 == 0 && W1 % 2 == 0, CFFM_E_UNSUPPORTED, "head_fuse: need C %% 8 == 0 and even H1, W1");
+  CFFM_REQUIRE(C % 64 == 0 && H1 % 2 == 0 && W1 % 2 == 0, CFFM_E_UNSUPPORTED, "head_fuse: need C %% 64 == 0 and even H1, W1");
   CFFM_REQUIRE((!c_half_f32 || ldh32 % 4 == 0) && (!c_half_f16 || ldh16 % 8 == 0), CFFM_E_BADARG, "head_fuse: bad stride");
   CFFM_REQUIRE(T_perm >= 0 && (T_perm <= 1 || N % T_perm == 0), CFFM_E_BADARG, "head_fuse: N=%d not a multiple of T_perm=%d", N, T_perm);
-  launch_k(head_fuse_kernel, grid_for(static_cast<int64_t>(N) * (H1 / 2) * (W1 / 2) * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream), 
+  launch_k(head_fuse_kernel, grid_for(static_cast<int64_t>(N) * (H1 / 2) * (W1 / 2) * (C / 64) * 32), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(p1), static_cast<const __half*>(p2), static_cast<const __half*>(p3),
       static_cast<const __half*>(p4), N, H1, W1, H2, W2, H3, W3, H4, W4, C, T_perm, shift, static_cast<__half*>(c_full),
       c_half_f32, ldh32, static_cast<__half*>(c_half_f16), ldh16);

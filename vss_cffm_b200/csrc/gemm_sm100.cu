@@ -169,6 +169,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* stg = reinterpret_cast<float*>(stg8);
     float* sbias = reinterpret_cast<float*>(stg8 + STG_BYTES - 256);   // [WCOLS <= 64] bias slice of this warp
     uint32_t it = 0;
+    float4 r4[NCH][8], r4n[NCH][8];                            // residual tile (+ the next one when BN == 64)
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int m0 = (t / n_tiles_n) * BLOCK_M, n0 = (t % n_tiles_n) * BN;
       const int wcol0 = n0 + ch * WCOLS;                       // first column of this warp
@@ -233,22 +234,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       // ---- general path: fp32 and/or fp16 output, optional fp32 residual (may alias out32)
       const int rsub = lane >> 3, csub = (lane & 7) * 4;       // after the transpose: 4 rows x 8 float4 per pass
-      float4 b4[NCH], r4[NCH][8];
+      float4 b4[NCH];
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int col = wcol0 + 32 * c + csub;
         b4[c] = (ep.bias != nullptr && col < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + col))
                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ep.residual != nullptr) {
+      }
+      // residual rows of tile `tt` in the post-transpose layout (independent of the accumulator)
+      auto load_residual = [&](int tt, float4 (&r)[NCH][8]) {
+        const int rm0 = (tt / n_tiles_n) * BLOCK_M + wq * 32 + rsub, rc0 = (tt % n_tiles_n) * BN + ch * WCOLS + csub;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int row = wrow0 + rsub + 4 * i;
-            r4[c][i] = (row < M && col < N)
-                           ? *reinterpret_cast<const float4*>(ep.residual + static_cast<int64_t>(row) * ep.ldr + col)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int row = rm0 + 4 * i, col = rc0 + 32 * c;
+            r[c][i] = (row < M && col < N)
+                          ? *reinterpret_cast<const float4*>(ep.residual + static_cast<int64_t>(row) * ep.ldr + col)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-        }
-      }
+      };
+      constexpr bool kPrefetchNext = (BN == 64);               // register budget: one extra residual tile only for BN=64
+      if (ep.residual != nullptr && (!kPrefetchNext || it == 0)) load_residual(t, r4);
       ptx::mbar_wait(&tfull_bar[acc], aph);
       ptx::tc_fence_after();
       uint32_t v[NCH][32];
@@ -259,6 +266,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if constexpr (kPrefetchNext) {                           // next tile's residual flies while this tile is stored
+        if (ep.residual != nullptr && t + static_cast<int>(gridDim.x) < n_tiles) load_residual(t + gridDim.x, r4n);
+      }
       if (dbg & 2) continue;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -293,6 +303,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
+      }
+      if constexpr (kPrefetchNext) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) r4[c][i] = r4n[c][i];
       }
     }
   }

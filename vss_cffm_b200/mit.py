@@ -205,22 +205,24 @@ class MixVisionTransformer(nn.Module):
                 # ---- efficient self-attention
                 ops.layernorm(xres, b["n1g"], b["n1b"], b["n1eps"], out16=xn)
                 q = ws.get(f"s{s}.q", (M, C), _H)
-                ops.gemm(xn, b["qw"], bias=b["qb"], out16=q)
                 sr = b["sr"]
-                if sr > 1:
-                    Hs, Ws_ = (Ho - sr) // sr + 1, (Wo - sr) // sr + 1
-                    Ms = N * Hs * Ws_
-                    scol = ws.get(f"s{s}.srcol", (Ms, sr * sr * C), _H)
-                    ops.im2col(xn, 1, N, Ho, Wo, C, sr, sr, 0, scol)
-                    s32 = ws.get(f"s{s}.sr32", (Ms, C), _F)
-                    ops.gemm(scol, b["srw"], bias=b["srb"], out32=s32)
-                    kvin = ws.get(f"s{s}.srn", (Ms, C), _H)
-                    ops.layernorm(s32, b["sng"], b["snb"], b["seps"], out16=kvin)
-                    nkv = Hs * Ws_
-                else:
-                    kvin, Ms, nkv = xn, M, Ho * Wo
-                kv = ws.get(f"s{s}.kv", (Ms, 2 * C), _H)
-                ops.gemm(kvin, b["kvw"], bias=b["kvb"], out16=kv)
+                with ops.fork():                                 # K/V chain on the side stream, q projection on the main one
+                    if sr > 1:
+                        Hs, Ws_ = (Ho - sr) // sr + 1, (Wo - sr) // sr + 1
+                        Ms = N * Hs * Ws_
+                        scol = ws.get(f"s{s}.srcol", (Ms, sr * sr * C), _H)
+                        ops.im2col(xn, 1, N, Ho, Wo, C, sr, sr, 0, scol)
+                        s32 = ws.get(f"s{s}.sr32", (Ms, C), _F)
+                        ops.gemm(scol, b["srw"], bias=b["srb"], out32=s32)
+                        kvin = ws.get(f"s{s}.srn", (Ms, C), _H)
+                        ops.layernorm(s32, b["sng"], b["snb"], b["seps"], out16=kvin)
+                        nkv = Hs * Ws_
+                    else:
+                        kvin, Ms, nkv = xn, M, Ho * Wo
+                    kv = ws.get(f"s{s}.kv", (Ms, 2 * C), _H)
+                    ops.gemm(kvin, b["kvw"], bias=b["kvb"], out16=kv)
+                ops.gemm(xn, b["qw"], bias=b["qb"], out16=q)
+                ops.join()
                 ao = ws.get(f"s{s}.ao", (M, C), _H)
                 ops.mha(q, kv[:, :C], kv[:, C:], ao, N, Ho * Wo, nkv, heads, d, d ** -0.5)
                 ops.gemm(ao, b["pw"], bias=b["pb"], residual=xres, out32=xres)

@@ -198,6 +198,36 @@ def softmax_nchw(x, out):
     _abi.call("cffm_softmax_nchw", _ptr(x), _ptr(out), B, C, h * w, _stream())
 
 
+_side = {}
+
+
+class fork:
+    """``with ops.fork(): ...`` enqueues the body on a side stream that first waits for everything already on the
+    current stream; ``ops.join()`` makes the current stream wait for it.  Independent branches of the forward (q
+    projection vs the spatial-reduction K/V chain, the four decoder projections, QKV vs pooling) then overlap on
+    the GPU; the fork/join pattern is preserved as parallel branches when the pass is captured in a CUDA graph."""
+
+    def __enter__(self):
+        dev = torch.cuda.current_device()
+        if dev not in _side:
+            _side[dev] = torch.cuda.Stream(device=dev)
+        self.side = _side[dev]
+        self.side.wait_stream(torch.cuda.current_stream())
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self.ctx.__exit__(*exc)
+        return False
+
+
+def join():
+    side = _side.get(torch.cuda.current_device())
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)
+
+
 class KernelTimer:
     """CUDA-event timing of selected entry points on the launching stream (bench.py's live roofline
     measurement).  ``with KernelTimer({"cffm_cfm_attention"}) as kt: step()`` then ``kt.results()``."""
