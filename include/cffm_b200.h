@@ -66,6 +66,16 @@ int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
                   float* out_f32, int64_t ldo32, int M, int N, int K, int act, int impl,
                   void* stream);
 
+/* GEMM with a LayerNorm fused into its epilogue, for N <= 128 (one tile spans the row):
+ *   x = A.W^T + bias (+ residual)  -> out_f32 (may be NULL; may alias residual);
+ *   LayerNorm(x; ln_gamma, ln_beta, ln_eps) -> ln_out_f16 (fp16 [M, ldln]).
+ * The MiT pairs "proj / fc2 + residual" followed by norm2 / next norm1 / the stage norm
+ * (mix_transformer.py:154-155,321-343) as one kernel instead of two. */
+int cffm_gemm_f16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                     const float* residual, int64_t ldr, float* out_f32, int64_t ldo32,
+                     const float* ln_gamma, const float* ln_beta, float ln_eps, void* ln_out_f16,
+                     int64_t ldln, int M, int N, int K, void* stream);
+
 /* Row LayerNorm over C channels, fp32 statistics.  x is fp32 (x_is_f32=1) or fp16.
  * Writes fp16 and/or fp32.  mix_transformer.py:154-155,198,321  cffm_transformer.py:824
  * swin_transformer_2d.py:619,622,663. */

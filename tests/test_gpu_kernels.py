@@ -382,3 +382,25 @@ def test_gelu_epilogue_accuracy(ops):
     ops.gemm(a, w, out32=out, act=ops.ACT_GELU)
     ref = F.gelu(a.double().cpu())
     assert (out.cpu().double() - ref).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 64), (300, 128, 256), (4100, 32, 32), (129, 64, 256), (513, 128, 512), (77, 8, 64)])
+def test_gemm_with_fused_layernorm(ops, M, N, K):
+    """x = A W^T + bias + residual (in place) and LayerNorm(x) in fp16 from ONE kernel == GEMM then LayerNorm."""
+    a = h16(synth.synth_array((M, K), 41)).cuda()
+    w = h16(synth.synth_array((N, K), 42, scale=K ** -0.5)).cuda()
+    bias = synth.synth_array((N,), 43).cuda()
+    res = synth.synth_array((M, N), 44, scale=2.0).cuda()
+    g, b = (synth.synth_array((N,), 45) * 0.1 + 1).cuda(), (synth.synth_array((N,), 46) * 0.1).cuda()
+    x_ref = a.double() @ w.double().t() + bias.double() + res.double()
+    for eps in (1e-5, 1e-6):
+        ln_ref = F.layer_norm(x_ref, (N,), g.double(), b.double(), eps)
+        x = res.clone()
+        ln = torch.empty(M, N, dtype=torch.float16, device="cuda")
+        ops.gemm_ln(a.half(), w.half(), bias, x, x, g, b, eps, ln)
+        check(x, x_ref, REL32, "fused gemm+ln: x")
+        check(ln, ln_ref, REL16, "fused gemm+ln: LayerNorm(x)")
+        ln2 = torch.empty_like(ln)
+        ops.gemm_ln(a.half(), w.half(), bias, res, None, g, b, eps, ln2)          # no fp32 output requested
+        assert torch.equal(ln, ln2)
+    assert ops.gemm_ln_supported(128) and not ops.gemm_ln_supported(320)

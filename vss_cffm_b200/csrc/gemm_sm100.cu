@@ -3,8 +3,8 @@
 // Persistent, warp-specialised, one CTA per SM looping over 128 x BN output tiles:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzled [rows][64] fp16 stages)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (2 accumulator stages in TMEM)
-//   warps 2..9  epilogue       (tcgen05.ld -> smem transpose -> bias / GELU / ReLU / fp32 residual ->
-//                               row-contiguous global stores), overlapped with the next tile's mainloop
+//   warps 2..17 epilogue       (tcgen05.ld -> smem transpose -> bias / GELU / ReLU / fp32 residual / LayerNorm
+//                               -> row-contiguous global stores), overlapped with the next tile's mainloop
 // Barriers: full[s] (TMA -> MMA, transaction bytes) / empty[s] (tcgen05.commit -> TMA),
 //           tfull[a] (tcgen05.commit -> epilogue) / tempty[a] (epilogue -> MMA).
 // Almost every GEMM of this path has K <= 256, i.e. it is HBM-bound: the design goal is bytes in
@@ -24,11 +24,11 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // 64 halves = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;                  // two per TMEM lane quarter
+constexpr int NUM_EPI_WARPS = 16;                 // four per TMEM lane quarter; one 32x32 chunk per warp per tile
 constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int STG_LD = 36;                        // padded fp32 row of the per-warp 32x32 transpose buffer
-constexpr int STG_BYTES = 32 * STG_LD * 4 + 768;   // 32x36 fp32 transpose buffer (or 32 x 144 B fp16 rows) + bias slice
+constexpr int STG_BYTES = 32 * STG_LD * 4 + 128;   // 32x36 fp32 transpose buffer (or 32 x 80 B fp16 rows) + 32-float bias slice
 
 struct Epilogue {
   const float* bias;
@@ -39,15 +39,24 @@ struct Epilogue {
   float* out32;
   int64_t ldo32;
   int act;
+  // optional fused LayerNorm of the output row (only when one tile spans the whole row: N <= BN)
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
+  __half* ln_out16;
+  int64_t ldln;
 };
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN == 64) ? 6 : 4;
+  static constexpr int STAGES = (BN == 64) ? 5 : 3;
+  static constexpr int TEAMS = (BN == 64) ? 2 : 1;  // BN=64: two 8-warp teams alternate tiles (accumulator stage = team)
+  static constexpr int TEAM_WARPS = NUM_EPI_WARPS / TEAMS;
   static constexpr int W_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + W_STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;        // double-buffered accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                    8192 /*LayerNorm row-statistics exchange*/;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -60,9 +69,9 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // share an A row-panel run at the same time and the panel is read from HBM once).
 //   warp 0      TMA producer: smem ring of STAGES x (A 128x64 | W BNx64), runs ahead across tiles
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, accumulator stage = tile parity
-//   warps 2..9  epilogue: tcgen05.ld (thread = row) -> per-warp smem transpose -> row-contiguous
-//               128-byte global accesses for residual / fp32 / fp16; overlaps the next tile's mainloop
-template <int BN, bool F16_ONLY>
+//   warps 2..17 epilogue: tcgen05.ld (thread = row) -> per-warp smem transpose -> row-contiguous
+//               global accesses for residual / fp32 / fp16 (+ optional fused LayerNorm); overlaps the mainloop
+template <int BN, bool F16_ONLY, bool LN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const Epilogue ep, const int M, const int N, const int K, const int n_tiles_n,
@@ -80,6 +89,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + C::STAGES;                 // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;                        // [2] accumulator drained
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* lnbuf = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + NUM_EPI_WARPS * STG_BYTES + 256);   // [2][4][2][32]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,7 +106,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
+      ptx::mbar_init(&tempty_bar[a], C::TEAM_WARPS);
     }
     ptx::fence_barrier_init();
   }
@@ -158,157 +168,186 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ===================== epilogue: TMEM -> regs -> smem transpose -> coalesced global =====================
-    // Warp (quarter wq, half ch) owns rows [32 wq, +32) x columns [ch BN/2, +BN/2) of the tile.  Everything that
-    // does not depend on the accumulator (bias, residual) is fetched BEFORE waiting for the MMA.
-    const int ew = warp - 2;                                   // 0..7
+    // 16 warps.  Warp (quarter wq, column group cg, team tm) owns the 32 x 32 chunk rows [32 wq, +32) x columns
+    // [32 cg, +32) of every tile of its team.  BN = 128: one team, cg = 0..3.  BN = 64: two teams (cg = 0..1) that
+    // alternate tiles, so two tiles are drained at once (accumulator stage = team).  Everything that does not
+    // depend on the accumulator (bias, residual) is fetched BEFORE waiting for the MMA.
+    const int ew = warp - 2;                                   // 0..15
     const int wq = warp & 3;                                   // TMEM lane quarter this warp may access
-    const int ch = ew >> 2;                                    // column half of the tile
-    constexpr int NCH = BN / 64;                               // 32-column chunks per warp (adjacent)
-    constexpr int WCOLS = NCH * 32;                            // columns per warp
+    const int cg = (ew >> 2) % (BN / 32);
+    const int tm = (ew >> 2) / (BN / 32);                      // 0 for BN = 128
     uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg_all) + ew * STG_BYTES;
     float* stg = reinterpret_cast<float*>(stg8);
-    float* sbias = reinterpret_cast<float*>(stg8 + STG_BYTES - 256);   // [WCOLS <= 64] bias slice of this warp
-    uint32_t it = 0;
-    float4 r4[NCH][8], r4n[NCH][8];                            // residual tile (+ the next one when BN == 64)
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    float* sbias = reinterpret_cast<float*>(stg8 + STG_BYTES - 128);   // [32] bias slice of this warp
+    const int rsub = lane >> 3, csub = (lane & 7) * 4;         // after the fp32 transpose: 4 rows x 8 float4 per pass
+    const int tstep = static_cast<int>(gridDim.x) * C::TEAMS;
+    uint32_t it = tm;
+    for (int t = blockIdx.x + tm * static_cast<int>(gridDim.x); t < n_tiles; t += tstep, it += C::TEAMS) {
       const int m0 = (t / n_tiles_n) * BLOCK_M, n0 = (t % n_tiles_n) * BN;
-      const int wcol0 = n0 + ch * WCOLS;                       // first column of this warp
+      const int wcol0 = n0 + cg * 32;                          // first column of this warp
       const int wrow0 = m0 + wq * 32;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + cg * 32;
       if (F16_ONLY) {
         // ---- fp16-only output (q / kv / qkv / fc1 / folded decoder projections)
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int col = wcol0 + 32 * c + lane;
-          sbias[32 * c + lane] = (ep.bias != nullptr && col < N) ? __ldg(ep.bias + col) : 0.f;
+        {
+          const int col = wcol0 + lane;
+          sbias[lane] = (ep.bias != nullptr && col < N) ? __ldg(ep.bias + col) : 0.f;
         }
         __syncwarp();
         ptx::mbar_wait(&tfull_bar[acc], aph);
         ptx::tc_fence_after();
-        uint32_t v[NCH][32];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-          ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + ch * WCOLS + 32 * c, v[c]);
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(taddr, v);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);     // registers hold the tile: MMA may reuse the stage
+        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);     // registers hold the chunk: MMA may reuse the stage
         if (dbg & 2) continue;                                 // probe: no epilogue work at all
         // bias + activation in the thread = row layout (bias is warp-uniform: broadcast LDS), pack to fp16 and
-        // stage [32 rows][WCOLS halves]; then each row is written with 16-byte lanes (WCOLS*2 contiguous bytes).
-        constexpr int P16 = WCOLS * 2 + 16;                    // padded row pitch (bytes): conflict-free STS.128
+        // stage [32 rows][64 B]; then 4 lanes write one row chunk (64 contiguous bytes), 8 rows per instruction.
+        constexpr int P16 = 80;                                // padded row pitch (bytes): conflict-free STS.128
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0 = *reinterpret_cast<const float4*>(sbias + 8 * j);
+          const float4 b1 = *reinterpret_cast<const float4*>(sbias + 8 * j + 4);
+          float a[8] = {__uint_as_float(v[8 * j]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
+                        __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
+                        __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
+                        __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
+          if (act != CFFM_ACT_NONE) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b0 = *reinterpret_cast<const float4*>(sbias + 32 * c + 8 * j);
-            const float4 b1 = *reinterpret_cast<const float4*>(sbias + 32 * c + 8 * j + 4);
-            float a[8] = {__uint_as_float(v[c][8 * j]) + b0.x, __uint_as_float(v[c][8 * j + 1]) + b0.y,
-                          __uint_as_float(v[c][8 * j + 2]) + b0.z, __uint_as_float(v[c][8 * j + 3]) + b0.w,
-                          __uint_as_float(v[c][8 * j + 4]) + b1.x, __uint_as_float(v[c][8 * j + 5]) + b1.y,
-                          __uint_as_float(v[c][8 * j + 6]) + b1.z, __uint_as_float(v[c][8 * j + 7]) + b1.w};
-            if (act != CFFM_ACT_NONE) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) a[e] = apply_act(a[e], act);
-            }
-            *reinterpret_cast<uint4*>(stg8 + lane * P16 + 64 * c + 16 * j) =
-                make_uint4(pack_half2(a[0], a[1]), pack_half2(a[2], a[3]), pack_half2(a[4], a[5]), pack_half2(a[6], a[7]));
+            for (int e = 0; e < 8; ++e) a[e] = apply_act(a[e], act);
           }
+          *reinterpret_cast<uint4*>(stg8 + lane * P16 + 16 * j) =
+              make_uint4(pack_half2(a[0], a[1]), pack_half2(a[2], a[3]), pack_half2(a[4], a[5]), pack_half2(a[6], a[7]));
         }
         __syncwarp();
-        constexpr int LPR = WCOLS / 8;                         // lanes per row (16-byte pieces): 4 or 8
-        constexpr int RPP = 32 / LPR;                          // rows per pass: 8 or 4
-        const int piece = lane % LPR, rr = lane / LPR;
+        const int piece = lane & 3, rr = lane >> 2;
         const int col = wcol0 + 8 * piece;
         if (col < N && !(dbg & 1)) {
           __half* obase = ep.out16 + static_cast<int64_t>(wrow0 + rr) * ep.ldo16 + col;
 #pragma unroll
-          for (int i = 0; i < LPR; ++i) {
-            const int row = wrow0 + rr + RPP * i;
-            const uint4 val = *reinterpret_cast<const uint4*>(stg8 + (rr + RPP * i) * P16 + 16 * piece);
-            if (row < M) *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(RPP * i) * ep.ldo16) = val;
+          for (int i = 0; i < 4; ++i) {
+            const int row = wrow0 + rr + 8 * i;
+            const uint4 val = *reinterpret_cast<const uint4*>(stg8 + (rr + 8 * i) * P16 + 16 * piece);
+            if (row < M) *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(8 * i) * ep.ldo16) = val;
           }
         }
         __syncwarp();                                          // staging buffer is re-used by the next tile
         continue;
       }
-      // ---- general path: fp32 and/or fp16 output, optional fp32 residual (may alias out32)
-      const int rsub = lane >> 3, csub = (lane & 7) * 4;       // after the transpose: 4 rows x 8 float4 per pass
-      float4 b4[NCH];
+      // ---- general path: fp32 and/or fp16 output, optional fp32 residual (may alias out32), optional LayerNorm
+      const int col = wcol0 + csub;                            // this lane's 4 columns after the transpose
+      const bool cvalid = col < N;                             // N % 8 == 0: the float4 is all-valid or all-invalid
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), r4[8];
+      if (ep.bias != nullptr && cvalid) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+      if (ep.residual != nullptr) {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int col = wcol0 + 32 * c + csub;
-        b4[c] = (ep.bias != nullptr && col < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + col))
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) {
+          const int row = wrow0 + rsub + 4 * i;
+          r4[i] = (row < M && cvalid) ? *reinterpret_cast<const float4*>(ep.residual + static_cast<int64_t>(row) * ep.ldr + col)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
-      // residual rows of tile `tt` in the post-transpose layout (independent of the accumulator)
-      auto load_residual = [&](int tt, float4 (&r)[NCH][8]) {
-        const int rm0 = (tt / n_tiles_n) * BLOCK_M + wq * 32 + rsub, rc0 = (tt % n_tiles_n) * BN + ch * WCOLS + csub;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = rm0 + 4 * i, col = rc0 + 32 * c;
-            r[c][i] = (row < M && col < N)
-                          ? *reinterpret_cast<const float4*>(ep.residual + static_cast<int64_t>(row) * ep.ldr + col)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-      };
-      constexpr bool kPrefetchNext = (BN == 64);               // register budget: one extra residual tile only for BN=64
-      if (ep.residual != nullptr && (!kPrefetchNext || it == 0)) load_residual(t, r4);
       ptx::mbar_wait(&tfull_bar[acc], aph);
       ptx::tc_fence_after();
-      uint32_t v[NCH][32];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c)
-        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + ch * WCOLS + 32 * c, v[c]);
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(taddr, v);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-      if constexpr (kPrefetchNext) {                           // next tile's residual flies while this tile is stored
-        if (ep.residual != nullptr && t + static_cast<int>(gridDim.x) < n_tiles) load_residual(t + gridDim.x, r4n);
-      }
       if (dbg & 2) continue;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int col = wcol0 + 32 * c + csub;                 // this lane's 4 columns after the transpose
-        __syncwarp();
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) =
+            make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                        __uint_as_float(v[4 * j + 3]));
+      __syncwarp();
+      float4 av[8];                                            // finished output values (kept for the fused LayerNorm)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) =
-              make_float4(__uint_as_float(v[c][4 * j]), __uint_as_float(v[c][4 * j + 1]),
-                          __uint_as_float(v[c][4 * j + 2]), __uint_as_float(v[c][4 * j + 3]));
-        __syncwarp();
-        if (col < N) {                                         // N % 8 == 0: the float4 is all-valid or all-invalid
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = wrow0 + rsub + 4 * i;
-            float4 a = *reinterpret_cast<const float4*>(stg + (rsub + 4 * i) * STG_LD + csub);
-            a.x += b4[c].x; a.y += b4[c].y; a.z += b4[c].z; a.w += b4[c].w;
-            if (act != CFFM_ACT_NONE) {
-              a.x = apply_act(a.x, act); a.y = apply_act(a.y, act);
-              a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
-            }
-            if (ep.residual != nullptr) { a.x += r4[c][i].x; a.y += r4[c][i].y; a.z += r4[c][i].z; a.w += r4[c][i].w; }
-            if (row < M && !(dbg & 1)) {
-              if (ep.out32 != nullptr)
-                *reinterpret_cast<float4*>(ep.out32 + static_cast<int64_t>(row) * ep.ldo32 + col) = a;
-              if (ep.out16 != nullptr) {
-                uint2 h;
-                h.x = pack_half2(a.x, a.y);
-                h.y = pack_half2(a.z, a.w);
-                *reinterpret_cast<uint2*>(ep.out16 + static_cast<int64_t>(row) * ep.ldo16 + col) = h;
-              }
-            }
+      for (int i = 0; i < 8; ++i) {
+        const int row = wrow0 + rsub + 4 * i;
+        float4 a = *reinterpret_cast<const float4*>(stg + (rsub + 4 * i) * STG_LD + csub);
+        a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+        if (act != CFFM_ACT_NONE) {
+          a.x = apply_act(a.x, act); a.y = apply_act(a.y, act);
+          a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
+        }
+        if (ep.residual != nullptr) { a.x += r4[i].x; a.y += r4[i].y; a.z += r4[i].z; a.w += r4[i].w; }
+        av[i] = a;
+        if (row < M && cvalid && !(dbg & 1)) {
+          if (ep.out32 != nullptr) *reinterpret_cast<float4*>(ep.out32 + static_cast<int64_t>(row) * ep.ldo32 + col) = a;
+          if (ep.out16 != nullptr) {
+            uint2 h;
+            h.x = pack_half2(a.x, a.y);
+            h.y = pack_half2(a.z, a.w);
+            *reinterpret_cast<uint2*>(ep.out16 + static_cast<int64_t>(row) * ep.ldo16 + col) = h;
           }
         }
       }
-      if constexpr (kPrefetchNext) {
+      __syncwarp();                                            // transpose buffer is re-used by the next tile
+      if constexpr (LN) {
+        // ---- fused LayerNorm over the N (<= BN) columns of each row.  A row lives in 8 lanes (same rsub) of each
+        // of the BN/32 warps of this (team, quarter): two-pass statistics, partial sums exchanged through shared
+        // memory with one named barrier per (team, quarter).
+        constexpr int NG = BN / 32;                            // warps sharing a row
+        const float invN = 1.f / static_cast<float>(N);
+        float* bsum = lnbuf + ((tm * 4 + wq) * 2 + 0) * (4 * 32);      // [cg][32 rows]
+        float* bsq = lnbuf + ((tm * 4 + wq) * 2 + 1) * (4 * 32);
+        const int bar_id = 1 + tm * 4 + wq;
+        float st[8], mean[8];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
+        for (int i = 0; i < 8; ++i) {
+          float sacc = cvalid ? (av[i].x + av[i].y) + (av[i].z + av[i].w) : 0.f;
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+          st[i] = sacc;
+        }
+        if ((lane & 7) == 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) r4[c][i] = r4n[c][i];
+          for (int i = 0; i < 8; ++i) bsum[cg * 32 + rsub + 4 * i] = st[i];
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NG * 32) : "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float tot = 0.f;
+#pragma unroll
+          for (int gq = 0; gq < NG; ++gq) tot += bsum[gq * 32 + rsub + 4 * i];
+          mean[i] = tot * invN;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dx = av[i].x - mean[i], dy = av[i].y - mean[i], dz = av[i].z - mean[i], dw = av[i].w - mean[i];
+          float sacc = cvalid ? (dx * dx + dy * dy) + (dz * dz + dw * dw) : 0.f;
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+          st[i] = sacc;
+        }
+        if ((lane & 7) == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bsq[cg * 32 + rsub + 4 * i] = st[i];
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NG * 32) : "memory");
+        if (cvalid) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + col));
+          const float4 be4 = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + col));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = wrow0 + rsub + 4 * i;
+            float tot = 0.f;
+#pragma unroll
+            for (int gq = 0; gq < NG; ++gq) tot += bsq[gq * 32 + rsub + 4 * i];
+            const float rstd = rsqrtf(tot * invN + ep.ln_eps);
+            uint2 h;
+            h.x = pack_half2((av[i].x - mean[i]) * rstd * g4.x + be4.x, (av[i].y - mean[i]) * rstd * g4.y + be4.y);
+            h.y = pack_half2((av[i].z - mean[i]) * rstd * g4.z + be4.z, (av[i].w - mean[i]) * rstd * g4.w + be4.w);
+            if (row < M && !(dbg & 1)) *reinterpret_cast<uint2*>(ep.ln_out16 + static_cast<int64_t>(row) * ep.ldln + col) = h;
+          }
+        }
       }
     }
   }
@@ -407,7 +446,7 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t K, int64_
   return CFFM_OK;
 }
 
-template <int BN, bool F16_ONLY>
+template <int BN, bool F16_ONLY, bool LN = false>
 int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const Epilogue& ep, int M, int N, int K,
                    cudaStream_t st) {
   CUtensorMap tmA, tmW;
@@ -418,14 +457,14 @@ int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, F16_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, F16_ONLY, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg<BN>::SMEM_BYTES);
   });
   CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
   const int tiles = tiles_n * tiles_m;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  launch_k(gemm_tcgen05_kernel<BN, F16_ONLY>, grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st, tmA, tmW, ep, M, N, K, tiles_n, tiles);
+  launch_k(gemm_tcgen05_kernel<BN, F16_ONLY, LN>, grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st, tmA, tmW, ep, M, N, K, tiles_n, tiles);
   return launch_status("gemm_tcgen05_kernel");
 }
 
@@ -448,7 +487,7 @@ extern "C" int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t 
                    (!residual || (ldr % 4 == 0 && ldr >= N)),
                CFFM_E_BADARG, "gemm: bad output/residual stride");
   CFFM_REQUIRE(act >= CFFM_ACT_NONE && act <= CFFM_ACT_RELU, CFFM_E_BADARG, "gemm: bad act %d", act);
-  Epilogue ep{bias, residual, ldr, static_cast<__half*>(out_f16), ldo16, out_f32, ldo32, act};
+  Epilogue ep{bias, residual, ldr, static_cast<__half*>(out_f16), ldo16, out_f32, ldo32, act, nullptr, nullptr, 0.f, nullptr, 0};
   if (const char* dbg = getenv("CFFM_GEMM_DEBUG")) ep.act |= atoi(dbg) << 8;   // bring-up experiments only (tools/gemm_probe.py)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (impl == CFFM_GEMM_CHECK) {
@@ -466,4 +505,27 @@ extern "C" int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t 
   }
   return wide ? launch_tcgen05<128, false>(A, lda, W, ldw, ep, M, N, K, st)
               : launch_tcgen05<64, false>(A, lda, W, ldw, ep, M, N, K, st);
+}
+
+extern "C" int cffm_gemm_f16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                const float* residual, int64_t ldr, float* out_f32, int64_t ldo32, const float* ln_gamma,
+                                const float* ln_beta, float ln_eps, void* ln_out_f16, int64_t ldln, int M, int N, int K,
+                                void* stream) {
+  using namespace cffm;
+  CFFM_REQUIRE(A && W && ln_gamma && ln_beta && ln_out_f16, CFFM_E_BADARG, "gemm_ln: null operand");
+  CFFM_REQUIRE(M > 0 && N > 0 && K > 0, CFFM_E_BADARG, "gemm_ln: non-positive size M=%d N=%d K=%d", M, N, K);
+  CFFM_REQUIRE(N <= 128, CFFM_E_UNSUPPORTED, "gemm_ln: the fused LayerNorm needs the whole row in one tile (N <= 128), got N=%d", N);
+  CFFM_REQUIRE(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, CFFM_E_UNSUPPORTED,
+               "gemm_ln: need K,N,lda,ldw multiples of 8 (M=%d N=%d K=%d)", M, N, K);
+  CFFM_REQUIRE(aligned16(A) && aligned16(W) && aligned16(bias) && aligned16(residual) && aligned16(out_f32) &&
+                   aligned16(ln_gamma) && aligned16(ln_beta) && (reinterpret_cast<uintptr_t>(ln_out_f16) & 7) == 0,
+               CFFM_E_BADARG, "gemm_ln: misaligned pointer");
+  CFFM_REQUIRE((!out_f32 || (ldo32 % 4 == 0 && ldo32 >= N)) && (!residual || (ldr % 4 == 0 && ldr >= N)) && ldln % 4 == 0 &&
+                   ldln >= N,
+               CFFM_E_BADARG, "gemm_ln: bad output/residual stride");
+  Epilogue ep{bias, residual, ldr, nullptr, 0, out_f32, ldo32, CFFM_ACT_NONE, ln_gamma, ln_beta, ln_eps,
+              static_cast<__half*>(ln_out_f16), ldln};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return N > 64 ? launch_tcgen05<128, false, true>(A, lda, W, ldw, ep, M, N, K, st)
+                : launch_tcgen05<64, false, true>(A, lda, W, ldw, ep, M, N, K, st);
 }

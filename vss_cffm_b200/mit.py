@@ -201,9 +201,13 @@ class MixVisionTransformer(nn.Module):
             xn = ws.get(f"s{s}.xn", (M, C), _H)
             heads = self.num_heads[s]
             d = C // heads
-            for b in st["blocks"]:
+            out = ws.get(f"s{s}.out", (M, C), _H)
+            fuse_ln = ops.gemm_ln_supported(C)                   # LayerNorm rides in the GEMM epilogue when N = C <= 128
+            nblk = len(st["blocks"])
+            for bi, b in enumerate(st["blocks"]):
                 # ---- efficient self-attention
-                ops.layernorm(xres, b["n1g"], b["n1b"], b["n1eps"], out16=xn)
+                if bi == 0 or not fuse_ln:
+                    ops.layernorm(xres, b["n1g"], b["n1b"], b["n1eps"], out16=xn)
                 q = ws.get(f"s{s}.q", (M, C), _H)
                 sr = b["sr"]
                 with ops.fork():                                 # K/V chain on the side stream, q projection on the main one
@@ -225,17 +229,29 @@ class MixVisionTransformer(nn.Module):
                 ops.join()
                 ao = ws.get(f"s{s}.ao", (M, C), _H)
                 ops.mha(q, kv[:, :C], kv[:, C:], ao, N, Ho * Wo, nkv, heads, d, d ** -0.5)
-                ops.gemm(ao, b["pw"], bias=b["pb"], residual=xres, out32=xres)
+                # ---- x += proj(attn) ; xn = norm2(x)   (one kernel when fusable)
+                if fuse_ln:
+                    ops.gemm_ln(ao, b["pw"], b["pb"], xres, xres, b["n2g"], b["n2b"], b["n2eps"], xn)
+                else:
+                    ops.gemm(ao, b["pw"], bias=b["pb"], residual=xres, out32=xres)
+                    ops.layernorm(xres, b["n2g"], b["n2b"], b["n2eps"], out16=xn)
                 # ---- Mix-FFN
-                ops.layernorm(xres, b["n2g"], b["n2b"], b["n2eps"], out16=xn)
                 Ch = b["f1w"].shape[0]
                 h1 = ws.get(f"s{s}.h1", (M, Ch), _H)
                 ops.gemm(xn, b["f1w"], bias=b["f1b"], out16=h1)
                 h2 = ws.get(f"s{s}.h2", (M, Ch), _H)
                 ops.dwconv3x3_gelu(h1, b["dww"], b["dwb"], h2, N, Ho, Wo, Ch)
-                ops.gemm(h2, b["f2w"], bias=b["f2b"], residual=xres, out32=xres)
-            out = ws.get(f"s{s}.out", (M, C), _H)
-            ops.layernorm(xres, st["fg"], st["fb"], st["feps"], out16=out)
+                # ---- x += fc2(...) ; then the next block's norm1 or the stage norm
+                if fuse_ln:
+                    if bi + 1 < nblk:
+                        nb = st["blocks"][bi + 1]
+                        ops.gemm_ln(h2, b["f2w"], b["f2b"], xres, xres, nb["n1g"], nb["n1b"], nb["n1eps"], xn)
+                    else:
+                        ops.gemm_ln(h2, b["f2w"], b["f2b"], xres, None, st["fg"], st["fb"], st["feps"], out)
+                else:
+                    ops.gemm(h2, b["f2w"], bias=b["f2b"], residual=xres, out32=xres)
+            if not fuse_ln or nblk == 0:
+                ops.layernorm(xres, st["fg"], st["fb"], st["feps"], out16=out)
             outs.append(out.view(N, Ho, Wo, C).permute(0, 3, 1, 2))   # logical NCHW, channels-last memory
             cur, layout, H, W = out, 1, Ho, Wo
         return outs

@@ -55,6 +55,28 @@ def gemm(a, w, bias=None, residual=None, out16=None, out32=None, act=ACT_NONE, i
               _ptr(out32), _ld(out32) if out32 is not None else 0, M, N, K, act, impl, _stream())
 
 
+def gemm_ln(a, w, bias, residual, out32, ln_gamma, ln_beta, ln_eps, ln_out16):
+    """x = a @ w.T + bias (+ residual) -> out32 (optional, may alias residual); LayerNorm(x) -> ln_out16.
+    Needs N <= 128 (``gemm_ln_supported``)."""
+    _chk(a, _H, "gemm_ln.a"); _chk(w, _H, "gemm_ln.w"); _chk(ln_out16, _H, "gemm_ln.ln_out16")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and tuple(ln_out16.shape) == (M, N) and ln_gamma.numel() == N == ln_beta.numel()
+    for t, n in ((bias, "bias"), (residual, "residual"), (out32, "out32"), (ln_gamma, "gamma"), (ln_beta, "beta")):
+        if t is not None:
+            _chk(t, _F, "gemm_ln." + n)
+    for t in (residual, out32):
+        if t is not None:
+            assert tuple(t.shape) == (M, N)
+    _abi.call("cffm_gemm_f16_ln", _ptr(a), _ld(a), _ptr(w), _ld(w), _ptr(bias), _ptr(residual),
+              _ld(residual) if residual is not None else 0, _ptr(out32), _ld(out32) if out32 is not None else 0,
+              _ptr(ln_gamma), _ptr(ln_beta), float(ln_eps), _ptr(ln_out16), _ld(ln_out16), M, N, K, _stream())
+
+
+def gemm_ln_supported(N):
+    return N <= 128 and N % 8 == 0
+
+
 def layernorm(x, gamma, beta, eps, out16=None, out32=None):
     """Row LayerNorm of x [M,C] (fp32 or fp16)."""
     assert x.dim() == 2 and x.dtype in (_H, _F)
