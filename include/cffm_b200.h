@@ -76,6 +76,23 @@ int cffm_gemm_f16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, con
                      const float* ln_gamma, const float* ln_beta, float ln_eps, void* ln_out_f16,
                      int64_t ldln, int M, int N, int K, void* stream);
 
+/* Split-K GEMM for the few-tile / long-K convolutions of the path (spatial-reduction conv
+ * mix_transformer.py:76,101-102 with K = sr*sr*C up to 4096; patch embeds of stages 3-4 with K = 9*C):
+ * split s covers a contiguous range of 64-wide k-blocks and writes its fp32 partial product to
+ * partials[s] ([splits, M, N] contiguous, no bias); cffm_layernorm_sum adds them in a fixed order
+ * (deterministic).  cffm_splitk_plan returns the split count to use (1 = do not split); it depends on K
+ * only, so that a row's summation order -- hence a clip's result -- does not change with the batch size. */
+int cffm_gemm_f16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* partials,
+                         int M, int N, int K, int splits, void* stream);
+int cffm_splitk_plan(int M, int N, int K);
+
+/* LayerNorm of x = sum_s partials[s] + bias (partials fp32 [nsum, M, C] contiguous; bias may be NULL):
+ * the reduction of cffm_gemm_f16_splitk fused into the LayerNorm that follows every such conv
+ * (mix_transformer.py:103,198). */
+int cffm_layernorm_sum(const float* partials, int nsum, const float* bias, const float* gamma,
+                       const float* beta, float eps, void* out_f16, int64_t ldo16, float* out_f32,
+                       int64_t ldo32, int M, int C, void* stream);
+
 /* Row LayerNorm over C channels, fp32 statistics.  x is fp32 (x_is_f32=1) or fp16.
  * Writes fp16 and/or fp32.  mix_transformer.py:154-155,198,321  cffm_transformer.py:824
  * swin_transformer_2d.py:619,622,663. */

@@ -404,3 +404,27 @@ def test_gemm_with_fused_layernorm(ops, M, N, K):
         ops.gemm_ln(a.half(), w.half(), bias, res, None, g, b, eps, ln2)          # no fp32 output requested
         assert torch.equal(ln, ln2)
     assert ops.gemm_ln_supported(128) and not ops.gemm_ln_supported(320)
+
+
+@pytest.mark.parametrize("M,N,K", [(1800, 64, 4096), (450, 512, 2880), (1800, 128, 2048), (225, 32, 2048), (300, 64, 512)])
+def test_splitk_gemm_and_summing_layernorm(ops, M, N, K):
+    """Split-K partial products + LayerNorm(sum + bias) == conv-as-GEMM followed by LayerNorm (mix_transformer.py:101-103)."""
+    a = h16(synth.synth_array((M, K), 51)).cuda()
+    w = h16(synth.synth_array((N, K), 52, scale=K ** -0.5)).cuda()
+    bias = synth.synth_array((N,), 53).cuda()
+    g, b = (synth.synth_array((N,), 54) * 0.1 + 1).cuda(), (synth.synth_array((N,), 55) * 0.1).cuda()
+    S = max(ops.splitk_plan(M, N, K), 2)
+    assert ops.splitk_plan(M, N, K) == ops.splitk_plan(7 * M, N, K)      # batch-size independent
+    parts = torch.full((S, M, N), float("nan"), dtype=torch.float32, device="cuda")
+    ops.gemm_splitk(a.half(), w.half(), parts)
+    x_ref = a.double() @ w.double().t()
+    check(parts.sum(0), x_ref, REL32, f"split-K partial sums (S={S})")
+    ln_ref = F.layer_norm(x_ref + bias.double(), (N,), g.double(), b.double(), 1e-5)
+    o16 = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    o32 = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.layernorm_sum(parts, bias, g, b, 1e-5, out16=o16, out32=o32)
+    check(o32, ln_ref, REL32, "layernorm_sum f32")
+    check(o16, ln_ref, REL16, "layernorm_sum f16")
+    o32b = torch.empty_like(o32)
+    ops.layernorm_sum(parts, bias, g, b, 1e-5, out32=o32b)
+    assert torch.equal(o32, o32b)                                  # fixed summation order: deterministic

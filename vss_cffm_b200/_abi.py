@@ -29,6 +29,9 @@ SIGNATURES = {
     "cffm_current_device": ([], i32),
     "cffm_gemm_f16": ([vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp], i32),
     "cffm_gemm_f16_ln": ([vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, vp, f32, vp, i64, i32, i32, i32, vp], i32),
+    "cffm_gemm_f16_splitk": ([vp, i64, vp, i64, vp, i32, i32, i32, i32, vp], i32),
+    "cffm_splitk_plan": ([i32, i32, i32], i32),
+    "cffm_layernorm_sum": ([vp, i32, vp, vp, vp, f32, vp, i64, vp, i64, i32, i32, vp], i32),
     "cffm_layernorm": ([vp, i32, i64, vp, vp, f32, vp, i64, vp, i64, i32, i32, vp], i32),
     "cffm_im2col": ([vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp], i32),
     "cffm_mha_f16": ([vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, f32, vp], i32),

@@ -30,7 +30,8 @@ template <bool IN_F32, int L, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ xin, int64_t ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ o16, int64_t ldo16,
-                 float* __restrict__ o32, int64_t ldo32, int M, int C) {
+                 float* __restrict__ o32, int64_t ldo32, int M, int C, int nsum, int64_t sum_stride,
+                 const float* __restrict__ sum_bias) {
   pdl_sync();
   constexpr int RPW = 32 / L;                                  // rows per warp
   const int lane = threadIdx.x & 31;
@@ -57,7 +58,16 @@ layernorm_kernel(const void* __restrict__ xin, int64_t ldx, const float* __restr
       x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (rv && v < nvec) {
         if (IN_F32) {
-          x[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(xin) + row * ldx + 4 * v);
+          const float* px = static_cast<const float*>(xin) + row * ldx + 4 * v;
+          x[i] = *reinterpret_cast<const float4*>(px);
+          for (int sp = 1; sp < nsum; ++sp) {                   // split-K partial sums (fixed order: deterministic)
+            const float4 t = *reinterpret_cast<const float4*>(px + sp * sum_stride);
+            x[i].x += t.x; x[i].y += t.y; x[i].z += t.z; x[i].w += t.w;
+          }
+          if (sum_bias != nullptr) {
+            const float4 t = *reinterpret_cast<const float4*>(sum_bias + 4 * v);
+            x[i].x += t.x; x[i].y += t.y; x[i].z += t.z; x[i].w += t.w;
+          }
         } else {
           const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const __half*>(xin) + row * ldx + 4 * v);
           const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
@@ -577,13 +587,15 @@ using namespace cffm;
 
 template <bool F32, int L, int NV>
 static void launch_ln(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, __half* o16,
-                      int64_t ldo16, float* o32, int64_t ldo32, int M, int C, cudaStream_t st) {
+                      int64_t ldo16, float* o32, int64_t ldo32, int M, int C, cudaStream_t st, int nsum = 1,
+                      int64_t sum_stride = 0, const float* sum_bias = nullptr) {
   constexpr int RPW = 32 / L;
   const int64_t warps = (static_cast<int64_t>(M) + RPW - 1) / RPW;
   int64_t grid = (warps + 7) / 8;
   const int64_t cap = 148 * 8 * 4;                             // 8 resident CTAs per SM, a few rows per warp
   if (grid > cap) grid = cap;
-  launch_k(layernorm_kernel<F32, L, NV>, static_cast<int>(grid), 256, 0, st, x, ldx, gamma, beta, eps, o16, ldo16, o32, ldo32, M, C);
+  launch_k(layernorm_kernel<F32, L, NV>, static_cast<int>(grid), 256, 0, st, x, ldx, gamma, beta, eps, o16, ldo16, o32, ldo32, M, C,
+           nsum, sum_stride, sum_bias);
 }
 
 extern "C" int cffm_layernorm(const void* x, int x_is_f32, int64_t ldx, const float* gamma, const float* beta,
@@ -770,4 +782,28 @@ extern "C" int cffm_upsample2_argmax(const float* scores, int64_t ldc, int64_t* 
   dim3 grid((Wo + UP_TILE - 1) / UP_TILE, (Ho + UP_TILE - 1) / UP_TILE, B);
   launch_k(upsample2_argmax_kernel, grid, 256, smem, static_cast<cudaStream_t>(stream), scores, ldc, labels, h, w, ncls, Hm, Wm, Ho, Wo);
   return launch_status("upsample2_argmax_kernel");
+}
+
+extern "C" int cffm_layernorm_sum(const float* partials, int nsum, const float* bias, const float* gamma, const float* beta,
+                                  float eps, void* out_f16, int64_t ldo16, float* out_f32, int64_t ldo32, int M, int C,
+                                  void* stream) {
+  CFFM_REQUIRE(partials && gamma && beta && (out_f16 || out_f32), CFFM_E_BADARG, "layernorm_sum: null pointer");
+  CFFM_REQUIRE(M > 0 && C > 0 && nsum >= 1, CFFM_E_BADARG, "layernorm_sum: bad size");
+  CFFM_REQUIRE(C <= 512 && C % 4 == 0, CFFM_E_UNSUPPORTED, "layernorm_sum: need C %% 4 == 0 and C <= 512, got %d", C);
+  CFFM_REQUIRE((!out_f16 || ldo16 % 4 == 0) && (!out_f32 || ldo32 % 4 == 0) && aligned16(gamma) && aligned16(beta) &&
+                   aligned16(partials) && aligned16(bias) && (reinterpret_cast<uintptr_t>(out_f16) & 7) == 0 && aligned16(out_f32),
+               CFFM_E_BADARG, "layernorm_sum: misaligned pointer or stride");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __half* o16 = static_cast<__half*>(out_f16);
+  const int nvec = C / 4;
+  const int64_t stride = static_cast<int64_t>(M) * C;
+#define CFFM_LNS(L, NV) launch_ln<true, L, NV>(partials, C, gamma, beta, eps, o16, ldo16, out_f32, ldo32, M, C, st, nsum, stride, bias)
+  if (nvec <= 8) CFFM_LNS(8, 1);
+  else if (nvec <= 16) CFFM_LNS(16, 1);
+  else if (nvec <= 32) CFFM_LNS(32, 1);
+  else if (nvec <= 64) CFFM_LNS(32, 2);
+  else if (nvec <= 96) CFFM_LNS(32, 3);
+  else CFFM_LNS(32, 4);
+#undef CFFM_LNS
+  return launch_status("layernorm_kernel");
 }

@@ -45,6 +45,10 @@ struct Epilogue {
   float ln_eps;
   __half* ln_out16;
   int64_t ldln;
+  // split-K: tile t covers k-blocks [split * kb_per, +kb_per) and writes its partial sums to out32 + split * split_stride
+  int splits;
+  int kb_per;
+  int64_t split_stride;
 };
 
 template <int BN>
@@ -125,8 +129,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ===================== TMA producer =====================
       uint32_t g = 0;                                          // k-blocks issued so far (all tiles)
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int m0 = (t / n_tiles_n) * BLOCK_M, n0 = (t % n_tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        const int split = t % ep.splits, tt = t / ep.splits;
+        const int m0 = (tt / n_tiles_n) * BLOCK_M, n0 = (tt % n_tiles_n) * BN;
+        const int kb0 = split * ep.kb_per, kb1 = min(num_kb, kb0 + ep.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++g) {
           const uint32_t s = g % C::STAGES, ph = (g / C::STAGES) & 1u;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1u);              // slot free (passes on the first round)
           if (dbg & 4) {                                       // probe: W only
@@ -150,7 +156,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ptx::mbar_wait(&tempty_bar[acc], aph ^ 1u);            // epilogue drained this accumulator stage
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        const int kb0 = (t % ep.splits) * ep.kb_per, kb1 = min(num_kb, kb0 + ep.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++g) {
           const uint32_t s = g % C::STAGES, ph = (g / C::STAGES) & 1u;
           ptx::mbar_wait(&full_bar[s], ph);                    // TMA bytes have landed
           ptx::tc_fence_after();
@@ -159,7 +166,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 halves = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_f16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_f16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[s]);                     // frees the smem slot when the MMAs retire
         }
@@ -183,7 +190,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int tstep = static_cast<int>(gridDim.x) * C::TEAMS;
     uint32_t it = tm;
     for (int t = blockIdx.x + tm * static_cast<int>(gridDim.x); t < n_tiles; t += tstep, it += C::TEAMS) {
-      const int m0 = (t / n_tiles_n) * BLOCK_M, n0 = (t % n_tiles_n) * BN;
+      const int split = t % ep.splits, tt = t / ep.splits;
+      const int m0 = (tt / n_tiles_n) * BLOCK_M, n0 = (tt % n_tiles_n) * BN;
       const int wcol0 = n0 + cg * 32;                          // first column of this warp
       const int wrow0 = m0 + wq * 32;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
@@ -278,7 +286,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (ep.residual != nullptr) { a.x += r4[i].x; a.y += r4[i].y; a.z += r4[i].z; a.w += r4[i].w; }
         av[i] = a;
         if (row < M && cvalid && !(dbg & 1)) {
-          if (ep.out32 != nullptr) *reinterpret_cast<float4*>(ep.out32 + static_cast<int64_t>(row) * ep.ldo32 + col) = a;
+          if (ep.out32 != nullptr)
+            *reinterpret_cast<float4*>(ep.out32 + split * ep.split_stride + static_cast<int64_t>(row) * ep.ldo32 + col) = a;
           if (ep.out16 != nullptr) {
             uint2 h;
             h.x = pack_half2(a.x, a.y);
@@ -462,7 +471,7 @@ int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const
   });
   CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
-  const int tiles = tiles_n * tiles_m;
+  const int tiles = tiles_n * tiles_m * ep.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   launch_k(gemm_tcgen05_kernel<BN, F16_ONLY, LN>, grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st, tmA, tmW, ep, M, N, K, tiles_n, tiles);
   return launch_status("gemm_tcgen05_kernel");
@@ -487,7 +496,8 @@ extern "C" int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t 
                    (!residual || (ldr % 4 == 0 && ldr >= N)),
                CFFM_E_BADARG, "gemm: bad output/residual stride");
   CFFM_REQUIRE(act >= CFFM_ACT_NONE && act <= CFFM_ACT_RELU, CFFM_E_BADARG, "gemm: bad act %d", act);
-  Epilogue ep{bias, residual, ldr, static_cast<__half*>(out_f16), ldo16, out_f32, ldo32, act, nullptr, nullptr, 0.f, nullptr, 0};
+  Epilogue ep{bias, residual, ldr, static_cast<__half*>(out_f16), ldo16, out_f32, ldo32, act, nullptr, nullptr, 0.f, nullptr, 0,
+              1, (K + BLOCK_K - 1) / BLOCK_K, 0};
   if (const char* dbg = getenv("CFFM_GEMM_DEBUG")) ep.act |= atoi(dbg) << 8;   // bring-up experiments only (tools/gemm_probe.py)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (impl == CFFM_GEMM_CHECK) {
@@ -524,8 +534,41 @@ extern "C" int cffm_gemm_f16_ln(const void* A, int64_t lda, const void* W, int64
                    ldln >= N,
                CFFM_E_BADARG, "gemm_ln: bad output/residual stride");
   Epilogue ep{bias, residual, ldr, nullptr, 0, out_f32, ldo32, CFFM_ACT_NONE, ln_gamma, ln_beta, ln_eps,
-              static_cast<__half*>(ln_out_f16), ldln};
+              static_cast<__half*>(ln_out_f16), ldln, 1, (K + BLOCK_K - 1) / BLOCK_K, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return N > 64 ? launch_tcgen05<128, false, true>(A, lda, W, ldw, ep, M, N, K, st)
                 : launch_tcgen05<64, false, true>(A, lda, W, ldw, ep, M, N, K, st);
+}
+
+extern "C" int cffm_gemm_f16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* partials, int M, int N,
+                                    int K, int splits, void* stream) {
+  using namespace cffm;
+  CFFM_REQUIRE(A && W && partials, CFFM_E_BADARG, "gemm_splitk: null operand");
+  CFFM_REQUIRE(M > 0 && N > 0 && K > 0 && splits >= 1, CFFM_E_BADARG, "gemm_splitk: bad size M=%d N=%d K=%d S=%d", M, N, K, splits);
+  CFFM_REQUIRE(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, CFFM_E_UNSUPPORTED,
+               "gemm_splitk: need K,N,lda,ldw multiples of 8 (M=%d N=%d K=%d)", M, N, K);
+  CFFM_REQUIRE(aligned16(A) && aligned16(W) && aligned16(partials), CFFM_E_BADARG, "gemm_splitk: misaligned pointer");
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  CFFM_REQUIRE(splits <= num_kb, CFFM_E_BADARG, "gemm_splitk: %d splits for %d k-blocks", splits, num_kb);
+  const int kb_per = (num_kb + splits - 1) / splits;
+  CFFM_REQUIRE((splits - 1) * kb_per < num_kb, CFFM_E_BADARG, "gemm_splitk: empty split (use cffm_splitk_plan)");
+  Epilogue ep{nullptr, nullptr, 0, nullptr, 0, partials, N, CFFM_ACT_NONE, nullptr, nullptr, 0.f, nullptr, 0,
+              splits, kb_per, static_cast<int64_t>(M) * N};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool wide = N % 128 == 0 || (N % 64 != 0 && N > 64);
+  return wide ? launch_tcgen05<128, false>(A, lda, W, ldw, ep, M, N, K, st) : launch_tcgen05<64, false>(A, lda, W, ldw, ep, M, N, K, st);
+}
+
+extern "C" int cffm_splitk_plan(int M, int N, int K) {
+  // Split count for the long-K convolutions of the path.  It depends on K ONLY: the summation order of a row must not
+  // change with the batch size, or a clip would no longer produce bit-identical results alone and inside a batch.
+  // One split per 8 k-blocks (512 columns of K), at most 8: K = 4096 -> 8, 2880 -> 5, 2048 -> 4, 1152..1280 -> 2.
+  using namespace cffm;
+  (void)M; (void)N;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  int s = num_kb / 8;
+  if (s > 8) s = 8;
+  if (s < 1) s = 1;
+  const int kb_per = (num_kb + s - 1) / s;
+  return (num_kb + kb_per - 1) / kb_per;                       // no empty split
 }

@@ -194,10 +194,15 @@ class MixVisionTransformer(nn.Module):
             M = N * Ho * Wo
             col = ws.get(f"s{s}.col", (M, st["kpad"]), _H)
             ops.im2col(cur, layout, N, H, W, st["cin"], k, stride, pad, col)
-            pe32 = ws.get(f"s{s}.pe32", (M, C), _F)
-            ops.gemm(col, st["w"], bias=st["b"], out32=pe32)
             xres = ws.get(f"s{s}.x", (M, C), _F)                 # fp32 residual stream
-            ops.layernorm(pe32, st["ng"], st["nb"], st["eps"], out32=xres)
+            S = ops.splitk_plan(M, C, st["kpad"])                # few tiles x long K (stages 3-4): split K over the SMs
+            pe32 = ws.get(f"s{s}.pe32", (S, M, C), _F)
+            if S > 1:
+                ops.gemm_splitk(col, st["w"], pe32)
+                ops.layernorm_sum(pe32, st["b"], st["ng"], st["nb"], st["eps"], out32=xres)
+            else:
+                ops.gemm(col, st["w"], bias=st["b"], out32=pe32[0])
+                ops.layernorm(pe32[0], st["ng"], st["nb"], st["eps"], out32=xres)
             xn = ws.get(f"s{s}.xn", (M, C), _H)
             heads = self.num_heads[s]
             d = C // heads
@@ -216,10 +221,15 @@ class MixVisionTransformer(nn.Module):
                         Ms = N * Hs * Ws_
                         scol = ws.get(f"s{s}.srcol", (Ms, sr * sr * C), _H)
                         ops.im2col(xn, 1, N, Ho, Wo, C, sr, sr, 0, scol)
-                        s32 = ws.get(f"s{s}.sr32", (Ms, C), _F)
-                        ops.gemm(scol, b["srw"], bias=b["srb"], out32=s32)
+                        S = ops.splitk_plan(Ms, C, sr * sr * C)   # 15 tiles x K up to 4096: split K over the SMs
+                        s32 = ws.get(f"s{s}.sr32", (S, Ms, C), _F)
                         kvin = ws.get(f"s{s}.srn", (Ms, C), _H)
-                        ops.layernorm(s32, b["sng"], b["snb"], b["seps"], out16=kvin)
+                        if S > 1:
+                            ops.gemm_splitk(scol, b["srw"], s32)
+                            ops.layernorm_sum(s32, b["srb"], b["sng"], b["snb"], b["seps"], out16=kvin)
+                        else:
+                            ops.gemm(scol, b["srw"], bias=b["srb"], out32=s32[0])
+                            ops.layernorm(s32[0], b["sng"], b["snb"], b["seps"], out16=kvin)
                         nkv = Hs * Ws_
                     else:
                         kvin, Ms, nkv = xn, M, Ho * Wo

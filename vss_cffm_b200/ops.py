@@ -73,6 +73,32 @@ def gemm_ln(a, w, bias, residual, out32, ln_gamma, ln_beta, ln_eps, ln_out16):
               _ptr(ln_gamma), _ptr(ln_beta), float(ln_eps), _ptr(ln_out16), _ld(ln_out16), M, N, K, _stream())
 
 
+def splitk_plan(M, N, K):
+    """Number of K splits that fills the SMs for a few-tile / long-K GEMM (1 = do not split)."""
+    return int(_abi.load().cffm_splitk_plan(M, N, K))
+
+
+def gemm_splitk(a, w, partials):
+    """partials[s] = a[:, ks] @ w[:, ks].T for the s-th contiguous K range; partials fp32 [S, M, N] contiguous."""
+    _chk(a, _H, "gemm_splitk.a"); _chk(w, _H, "gemm_splitk.w"); _chk(partials, _F, "gemm_splitk.partials")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and partials.is_contiguous() and tuple(partials.shape[1:]) == (M, N)
+    _abi.call("cffm_gemm_f16_splitk", _ptr(a), _ld(a), _ptr(w), _ld(w), _ptr(partials), M, N, K, partials.shape[0], _stream())
+
+
+def layernorm_sum(partials, bias, gamma, beta, eps, out16=None, out32=None):
+    """LayerNorm(sum_s partials[s] + bias)."""
+    _chk(partials, _F, "layernorm_sum.partials")
+    S, M, C = partials.shape
+    assert partials.is_contiguous()
+    for t in (out16, out32):
+        if t is not None:
+            assert tuple(t.shape) == (M, C)
+    _abi.call("cffm_layernorm_sum", _ptr(partials), S, _ptr(bias), _ptr(gamma), _ptr(beta), float(eps), _ptr(out16),
+              _ld(out16) if out16 is not None else 0, _ptr(out32), _ld(out32) if out32 is not None else 0, M, C, _stream())
+
+
 def gemm_ln_supported(N):
     return N <= 128 and N % 8 == 0
 
