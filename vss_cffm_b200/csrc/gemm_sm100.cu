@@ -411,11 +411,13 @@ gemm_check_kernel(const __half* __restrict__ A, int64_t lda, const __half* __res
 }
 
 // ----------------------------------------------------------------------------------------------
+}  // namespace
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-EncodeTiledFn get_encode_fn() {
+static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -428,7 +430,7 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int num_sms() {
+int num_sms() {   // shared: common.cuh
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -440,7 +442,7 @@ int num_sms() {
 }
 
 // 2-D fp16 row-major [rows, K] with row stride ld (elements); box = [box_rows][64], 128-byte swizzle.
-int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {   // shared: common.cuh
   EncodeTiledFn fn = get_encode_fn();
   CFFM_REQUIRE(fn != nullptr, CFFM_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
@@ -454,6 +456,8 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t K, int64_
                static_cast<int>(r), (long long)rows, (long long)K, (long long)ld);
   return CFFM_OK;
 }
+
+namespace {
 
 template <int BN, bool F16_ONLY, bool LN = false>
 int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const Epilogue& ep, int M, int N, int K,
