@@ -138,6 +138,13 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// 2^x, one MUFU.EX2 (flush-to-zero, no range fix-up): softmax probabilities
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ------------------------------------------------------------------ legacy warp MMA (attention kernels)
 __device__ __forceinline__ void mma_m16n8k16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
