@@ -116,22 +116,22 @@ __global__ void __launch_bounds__(256)
 im2col_nhwc_kernel(const __half* __restrict__ x, int N, int H, int W, int C, int k, int stride, int pad, int Ho,
                    int Wo, __half* __restrict__ A, int Kpad) {
   pdl_sync();
-  const int chunks = Kpad / 8;
-  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * chunks;
-  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
-    const int ch = static_cast<int>(i % chunks);
-    const int64_t m = i / chunks;
-    const int kcol = ch * 8;
+  // 32-bit index arithmetic (the host checks that the chunk count fits): 64-bit divisions cost more than the copy
+  const uint32_t chunks = Kpad / 8;
+  const uint32_t total = static_cast<uint32_t>(N) * Ho * Wo * chunks;
+  const uint32_t kdim = k * k * C;
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total; i += 256u * gridDim.x) {
+    const uint32_t m = i / chunks, kcol = (i - m * chunks) * 8;
     uint4 val = make_uint4(0, 0, 0, 0);
-    if (kcol < k * k * C) {
-      const int tap = kcol / C, c = kcol % C;
-      const int ky = tap / k, kx = tap % k;
-      const int ox = static_cast<int>(m % Wo), oy = static_cast<int>((m / Wo) % Ho), n = static_cast<int>(m / (Wo * Ho));
-      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+    if (kcol < kdim) {
+      const uint32_t tap = kcol / C, c = kcol - tap * C;
+      const uint32_t ky = tap / k, kx = tap - ky * k;
+      const uint32_t t = m / Wo, ox = m - t * Wo, n = t / Ho, oy = t - n * Ho;
+      const int iy = static_cast<int>(oy * stride + ky) - pad, ix = static_cast<int>(ox * stride + kx) - pad;
       if (iy >= 0 && iy < H && ix >= 0 && ix < W)
         val = *reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * C + c);
     }
-    *reinterpret_cast<uint4*>(A + m * Kpad + kcol) = val;
+    *reinterpret_cast<uint4*>(A + static_cast<int64_t>(m) * Kpad + kcol) = val;
   }
 }
 
@@ -184,68 +184,126 @@ im2col_nchw_f32_kernel(const float* __restrict__ x, int N, int H, int W, int C, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 3x3 (pad 1) + bias + GELU, NHWC fp16.  One thread = 8 channels x a strip of 4 horizontally
-// adjacent pixels: each input row of the strip is loaded once (6 x 16 B) and re-used by the 3 horizontal
-// taps of 4 outputs (4.5 loads per output instead of 9); a warp reads 512 contiguous bytes per tap at C=256.
-constexpr int DW_PX = 4;
-__global__ void __launch_bounds__(256)
-dwconv3x3_gelu_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
-                      __half* __restrict__ out, int N, int H, int W, int C) {
-  pdl_sync();
-  const int chunks = C / 8, strips = (W + DW_PX - 1) / DW_PX;
-  const int64_t total = static_cast<int64_t>(N) * H * strips * chunks;
-  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
-    const int c = static_cast<int>(i % chunks) * 8;
-    const int64_t p = i / chunks;
-    const int x0 = static_cast<int>(p % strips) * DW_PX, yy = static_cast<int>((p / strips) % H);
-    const int n = static_cast<int>(p / (static_cast<int64_t>(strips) * H));
-    float acc[DW_PX][8];
-    {
-      const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+// depthwise 3x3 (pad 1) + bias + exact GELU, NHWC fp16 (Mix-FFN, mix_transformer.py:20-55).
+// One thread = CPT channels x a PXW-pixel-wide column strip of RS output rows.  Every input
+// row of the strip is loaded ONCE ((PXW + 2) vectors) and feeds the three output rows that see it through ky = 0, 1, 2
+// (three rotating fp32 accumulator rows); weights and bias live in registers for the whole strip.  ~1.4 loads and
+// conversions per output instead of 4.5, 32-bit index arithmetic, loops fully unrolled (static register rotation).
+template <int CPT> struct HalfVec;
+template <> struct HalfVec<2> { using T = uint32_t; };
+template <> struct HalfVec<4> { using T = uint2; };
+template <> struct HalfVec<8> { using T = uint4; };
+
+template <int CPT>
+__device__ __forceinline__ void load_halves(const __half* __restrict__ p, float* f) {
+  const typename HalfVec<CPT>::T raw = *reinterpret_cast<const typename HalfVec<CPT>::T*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-      for (int q = 0; q < DW_PX; ++q) {
-        acc[q][0] = b0.x; acc[q][1] = b0.y; acc[q][2] = b0.z; acc[q][3] = b0.w;
-        acc[q][4] = b1.x; acc[q][5] = b1.y; acc[q][6] = b1.z; acc[q][7] = b1.w;
+  for (int i = 0; i < CPT / 2; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+template <int CPT>
+__device__ __forceinline__ void store_halves(__half* __restrict__ p, const float* f) {
+  typename HalfVec<CPT>::T raw;
+  __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < CPT / 2; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<typename HalfVec<CPT>::T*>(p) = raw;
+}
+
+// One column strip.  INTERIOR: all PXW + 2 input columns and all PXW output columns are inside the image, so no
+// per-column predicates; CT > 0: the channel count is a compile-time constant and every load / store of a row is
+// `row pointer + immediate` (the integer address arithmetic was ~35 % of the issued instructions before).
+template <int CPT, int PXW, int RS, int CT, bool INTERIOR>
+__device__ __forceinline__ void dwconv_strip(const __half* __restrict__ xin_n, __half* __restrict__ out_n,
+                                             const float (&wf)[9][CPT], const float (&bs)[CPT], int x0, int y0, int H,
+                                             int W, int C_rt) {
+  const int C = CT > 0 ? CT : C_rt;
+  const int64_t row_stride = static_cast<int64_t>(W) * C;
+  const __half* rp = xin_n + (static_cast<int64_t>(y0 - 1) * W + (x0 - 1)) * C;   // input row y0 - 1, column x0 - 1
+  __half* op = out_n + (static_cast<int64_t>(y0) * W + x0) * C;
+  float acc[3][PXW][CPT];
+#pragma unroll
+  for (int r = 0; r < RS + 2; ++r, rp += row_stride) {
+    const int iy = y0 - 1 + r;
+    if (iy >= 0 && iy < H) {
+      float xin[PXW + 2][CPT];
+#pragma unroll
+      for (int j = 0; j < PXW + 2; ++j) {
+        if (INTERIOR || (x0 - 1 + j >= 0 && x0 - 1 + j < W)) load_halves<CPT>(rp + j * C, xin[j]);
+        else {
+#pragma unroll
+          for (int e = 0; e < CPT; ++e) xin[j][e] = 0.f;
+        }
       }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int q = r - ky;                                   // output row (relative) that sees this input row through ky
+        if (q >= 0 && q < RS) {
+#pragma unroll
+          for (int px = 0; px < PXW; ++px)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+              for (int e = 0; e < CPT; ++e) {
+                // the first tap of an output row starts from the bias (row q opens with input row r = q, ky = 0, kx = 0)
+                const float prev = (ky == 0 && kx == 0) ? bs[e] : acc[q % 3][px][e];
+                acc[q % 3][px][e] = fmaf(xin[px + kx][e], wf[ky * 3 + kx][e], prev);
+              }
+        }
+      }
+    } else if (r < RS) {                                        // zero-padding row above the image: row q = r opens with the bias
+#pragma unroll
+      for (int px = 0; px < PXW; ++px)
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) acc[r % 3][px][e] = bs[e];
     }
+    if (r >= 2) {                                               // output row q = r - 2 is complete
+      if (y0 + r - 2 < H) {
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = yy + ky - 1;
-      if (iy < 0 || iy >= H) continue;
-      const __half* row = x + (static_cast<int64_t>(n) * H + iy) * W * C + c;
-      half8 xv[DW_PX + 2];
+        for (int px = 0; px < PXW; ++px) {
+          if (INTERIOR || x0 + px < W) {
+            float o[CPT];
 #pragma unroll
-      for (int j = 0; j < DW_PX + 2; ++j) {
-        const int ix = x0 + j - 1;
-        if (ix >= 0 && ix < W) xv[j] = *reinterpret_cast<const half8*>(row + static_cast<int64_t>(ix) * C);
-        else { xv[j].h[0] = xv[j].h[1] = xv[j].h[2] = xv[j].h[3] = __floats2half2_rn(0.f, 0.f); }
-      }
-      float wf[3][8];
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) unpack8(*reinterpret_cast<const half8*>(w + (ky * 3 + kx) * C + c), wf[kx]);
-#pragma unroll
-      for (int j = 0; j < DW_PX + 2; ++j) {
-        float xf[8];
-        unpack8(xv[j], xf);
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int q = j - kx;                                 // output pixel that sees column j through tap kx
-          if (q >= 0 && q < DW_PX) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[q][e] = fmaf(xf[e], wf[kx][e], acc[q][e]);
+            for (int e = 0; e < CPT; ++e) o[e] = gelu_erf(acc[(r - 2) % 3][px][e]);
+            store_halves<CPT>(op + px * C, o);
           }
         }
       }
-    }
-#pragma unroll
-    for (int q = 0; q < DW_PX; ++q) {
-      if (x0 + q < W) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[q][e] = gelu_erf(acc[q][e]);
-        *reinterpret_cast<half8*>(out + ((static_cast<int64_t>(n) * H + yy) * W + x0 + q) * C + c) = pack8(acc[q]);
-      }
+      op += row_stride;
     }
   }
+}
+
+template <int CPT, int PXW, int RS, int CT>
+__global__ void __launch_bounds__(256)
+dwconv3x3_gelu_rows_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
+                           __half* __restrict__ out, int N, int H, int W, int C_rt, int strips_x, int strips_y) {
+  pdl_sync();
+  const int C = CT > 0 ? CT : C_rt;
+  const uint32_t chunks = C / CPT;
+  uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+  if (idx >= static_cast<uint32_t>(N) * strips_y * strips_x * chunks) return;
+  const uint32_t cc = idx % chunks; idx /= chunks;
+  const uint32_t xs = idx % strips_x; idx /= strips_x;
+  const uint32_t ys = idx % strips_y, n = idx / strips_y;
+  const int c = cc * CPT, x0 = xs * PXW, y0 = ys * RS;
+  float wf[9][CPT], bs[CPT];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) load_halves<CPT>(w + t * C + c, wf[t]);
+#pragma unroll
+  for (int e = 0; e < CPT; e += 2) {
+    const float2 b2 = *reinterpret_cast<const float2*>(bias + c + e);
+    bs[e] = b2.x; bs[e + 1] = b2.y;
+  }
+  const __half* xin_n = x + static_cast<int64_t>(n) * H * W * C + c;
+  __half* out_n = out + static_cast<int64_t>(n) * H * W * C + c;
+  if (x0 >= 1 && x0 + PXW + 1 <= W) dwconv_strip<CPT, PXW, RS, CT, true>(xin_n, out_n, wf, bs, x0, y0, H, W, C);
+  else dwconv_strip<CPT, PXW, RS, CT, false>(xin_n, out_n, wf, bs, x0, y0, H, W, C);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -277,17 +335,17 @@ head_fuse_kernel(const __half* __restrict__ p1, const __half* __restrict__ p2, c
                  int C, int Tperm, const float* __restrict__ shift, __half* __restrict__ c_full,
                  float* __restrict__ h32, int64_t ldh32, __half* __restrict__ h16, int64_t ldh16) {
   pdl_sync();
-  const int groups = C / 64, Hh = H1 / 2, Wh = W1 / 2;
-  const int64_t total_warps = static_cast<int64_t>(N) * Hh * Wh * groups;
+  const uint32_t groups = C / 64, Hh = H1 / 2, Wh = W1 / 2;
+  const uint32_t total_warps = static_cast<uint32_t>(N) * Hh * Wh * groups;   // host checks that it fits 32 bits
   const float sy2 = static_cast<float>(H2) / H1, sx2 = static_cast<float>(W2) / W1;
   const float sy3 = static_cast<float>(H3) / H1, sx3 = static_cast<float>(W3) / W1;
   const float sy4 = static_cast<float>(H4) / H1, sx4 = static_cast<float>(W4) / W1;
   const int lane = threadIdx.x & 31, q = lane >> 3, cc = lane & 7;
-  const int64_t warp0 = (blockIdx.x * 256ll + threadIdx.x) >> 5, nwarps = (gridDim.x * 256ll) >> 5;
-  for (int64_t wi = warp0; wi < total_warps; wi += nwarps) {
-    const int g = static_cast<int>(wi % groups);
-    const int64_t p = wi / groups;
-    const int xh = static_cast<int>(p % Wh), yh = static_cast<int>((p / Wh) % Hh), n = static_cast<int>(p / (Wh * Hh));
+  for (uint32_t wi = (blockIdx.x * 256u + threadIdx.x) >> 5; wi < total_warps; wi += (gridDim.x * 256u) >> 5) {
+    uint32_t p = wi / groups;
+    const int g = static_cast<int>(wi - p * groups);
+    const int xh = static_cast<int>(p % Wh); p /= Wh;
+    const int yh = static_cast<int>(p % Hh), n = static_cast<int>(p / Hh);
     // input frame n = b*T + t (reference order) -> output slot t*B + b (frame-major, targets last)
     const int no = Tperm > 1 ? (n % Tperm) * (N / Tperm) + n / Tperm : n;
     const int c = g * 64 + cc * 8;
@@ -323,6 +381,119 @@ head_fuse_kernel(const __half* __restrict__ p1, const __half* __restrict__ p2, c
       if (h16) *reinterpret_cast<half8*>(h16 + po * ldh16 + c) = pack8(acc);
     }
   }
+}
+
+// Same operation for an exact feature pyramid (H2 = H1/2, H3 = H1/4, H4 = H1/8, likewise W): one thread = one
+// half-resolution pixel (2 x 2 full-resolution pixels) x 8 channels.  With exact power-of-two ratios the four pixels
+// of a block interpolate inside ONE 3 x 3 neighbourhood of p2 and ONE 2 x 2 neighbourhood of p3 and of p4, so a
+// block needs 4 + 9 + 4 + 4 = 21 sixteen-byte loads instead of 4 x 13, the horizontal interpolation of a tap row is
+// shared by the two pixel rows, and the 2 x 2 mean stays in registers (no shuffles).  Interpolation weights still
+// come from lerp_coord() (border clamps included); only the tap indices use the closed form.
+__device__ __forceinline__ void ld8f(const __half* __restrict__ p, float* f) {
+  unpack8(*reinterpret_cast<const half8*>(p), f);
+}
+
+__global__ void __launch_bounds__(256)
+head_fuse_pyramid_kernel(const __half* __restrict__ p1, const __half* __restrict__ p2, const __half* __restrict__ p3,
+                         const __half* __restrict__ p4, int N, int H1, int W1, int C, int Tperm,
+                         const float* __restrict__ shift, __half* __restrict__ c_full, float* __restrict__ h32,
+                         int64_t ldh32, __half* __restrict__ h16, int64_t ldh16) {
+  pdl_sync();
+  const uint32_t chunks = C / 8, Hh = H1 / 2, Wh = W1 / 2;
+  uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+  if (idx >= static_cast<uint32_t>(N) * Hh * Wh * chunks) return;
+  const int c = static_cast<int>(idx % chunks) * 8; idx /= chunks;
+  const int xh = static_cast<int>(idx % Wh); idx /= Wh;
+  const int yh = static_cast<int>(idx % Hh), n = static_cast<int>(idx / Hh);
+  const int no = Tperm > 1 ? (n % Tperm) * (N / Tperm) + n / Tperm : n;   // clip-major input -> frame-major output
+  float acc[2][2][8];
+  {
+    const float4 s0 = *reinterpret_cast<const float4*>(shift + c), s1 = *reinterpret_cast<const float4*>(shift + c + 4);
+    const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const __half* b1 = p1 + ((static_cast<int64_t>(n) * H1 + 2 * yh) * W1 + 2 * xh) * C + c;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        ld8f(b1 + (static_cast<int64_t>(dy) * W1 + dx) * C, acc[dy][dx]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[dy][dx][e] += sh[e];
+      }
+  }
+  {   // ---- p2 (x2): rows / columns {h-1, h, h+1} clamped; pixel 0 uses taps (0,1), pixel 1 uses taps (1,2)
+    const int H2 = Hh, W2 = Wh;
+    const Lerp ly0 = lerp_coord(2 * yh, 0.5f, H2), ly1 = lerp_coord(2 * yh + 1, 0.5f, H2);
+    const Lerp lx0 = lerp_coord(2 * xh, 0.5f, W2), lx1 = lerp_coord(2 * xh + 1, 0.5f, W2);
+    const int rows[3] = {max(yh - 1, 0), yh, min(yh + 1, H2 - 1)};
+    const int cols[3] = {max(xh - 1, 0), xh, min(xh + 1, W2 - 1)};
+    const __half* base = p2 + static_cast<int64_t>(n) * H2 * W2 * C + c;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float t[3][8], hx[2][8];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ld8f(base + (static_cast<int64_t>(rows[r]) * W2 + cols[k]) * C, t[k]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        hx[0][e] = lx0.w0 * t[0][e] + lx0.w1 * t[1][e];
+        hx[1][e] = lx1.w0 * t[1][e] + lx1.w1 * t[2][e];
+      }
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (r == 0) acc[0][dx][e] = fmaf(ly0.w0, hx[dx][e], acc[0][dx][e]);
+          if (r == 1) { acc[0][dx][e] = fmaf(ly0.w1, hx[dx][e], acc[0][dx][e]); acc[1][dx][e] = fmaf(ly1.w0, hx[dx][e], acc[1][dx][e]); }
+          if (r == 2) acc[1][dx][e] = fmaf(ly1.w1, hx[dx][e], acc[1][dx][e]);
+        }
+    }
+  }
+#pragma unroll
+  for (int lvl = 0; lvl < 2; ++lvl) {   // ---- p3 (x4), p4 (x8): the four pixels share one 2 x 2 tap neighbourhood
+    const int Hs = lvl == 0 ? H1 / 4 : H1 / 8, Ws = lvl == 0 ? W1 / 4 : W1 / 8;
+    const float sc = lvl == 0 ? 0.25f : 0.125f;
+    const __half* base = (lvl == 0 ? p3 : p4) + static_cast<int64_t>(n) * Hs * Ws * C + c;
+    const Lerp ly0 = lerp_coord(2 * yh, sc, Hs), ly1 = lerp_coord(2 * yh + 1, sc, Hs);
+    const Lerp lx0 = lerp_coord(2 * xh, sc, Ws), lx1 = lerp_coord(2 * xh + 1, sc, Ws);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float t[2][8], hx[2][8];
+      const int row = r == 0 ? ly0.i0 : ly0.i1;
+      ld8f(base + (static_cast<int64_t>(row) * Ws + lx0.i0) * C, t[0]);
+      ld8f(base + (static_cast<int64_t>(row) * Ws + lx0.i1) * C, t[1]);
+      const float wy0 = r == 0 ? ly0.w0 : ly0.w1, wy1 = r == 0 ? ly1.w0 : ly1.w1;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        hx[0][e] = lx0.w0 * t[0][e] + lx0.w1 * t[1][e];
+        hx[1][e] = lx1.w0 * t[0][e] + lx1.w1 * t[1][e];
+      }
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          acc[0][dx][e] = fmaf(wy0, hx[dx][e], acc[0][dx][e]);
+          acc[1][dx][e] = fmaf(wy1, hx[dx][e], acc[1][dx][e]);
+        }
+    }
+  }
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[dy][dx][e] = fmaxf(acc[dy][dx][e], 0.f);
+      if (c_full)
+        *reinterpret_cast<half8*>(c_full + ((static_cast<int64_t>(no) * H1 + 2 * yh + dy) * W1 + 2 * xh + dx) * C + c) = pack8(acc[dy][dx]);
+    }
+  float m[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m[e] = ((acc[0][0][e] + acc[0][1][e]) + (acc[1][0][e] + acc[1][1][e])) * 0.25f;
+  const int64_t po = (static_cast<int64_t>(no) * Hh + yh) * Wh + xh;
+  if (h32) {
+    float* o = h32 + po * ldh32 + c;
+    *reinterpret_cast<float4*>(o) = make_float4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(m[4], m[5], m[6], m[7]);
+  }
+  if (h16) *reinterpret_cast<half8*>(h16 + po * ldh16 + c) = pack8(m);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -402,7 +573,7 @@ cffa_pool_kernel(const __half* __restrict__ xn, int B, int T, int H, int W, int 
       for (int v = 0; v < WS; ++v) {                              // 7 independent loads in flight
         const int xx = WS * px + v;
         if (y < H && xx < W) row[v] = *reinterpret_cast<const half8*>(src + (static_cast<int64_t>(y) * W + xx) * C);
-        else row[v].h[0] = row[v].h[1] = row[v].h[2] = row[v].h[3] = __floats2half2_rn(0.f, 0.f);
+        else row[v] = zero_half8();
       }
 #pragma unroll
       for (int v = 0; v < WS; ++v) {
@@ -574,6 +745,104 @@ upsample2_argmax_kernel(const float* __restrict__ lg, int64_t ldc, int64_t* __re
   labels[(static_cast<int64_t>(b) * Ho + Y) * Wo + X] = arg;
 }
 
+// Fast path of the same operation for the production geometry: exact x2 (h -> 2h) followed by exact x4 (2h -> 8h).
+// Output pixels Y = 4 cy + 2 + j (j = 0..3) all interpolate between the intermediate rows cy and cy + 1 (clamped), so a
+// "cell" (cy, cx) owns a 4 x 4 block of output pixels whose four corner values are read ONCE per class; the horizontal
+// interpolation is shared by the 4 rows.  One CTA = 8 x 8 cells x 4 class groups (thread = cell x group, classes
+// c = 4 i + g): ~6.5 instructions per (pixel, class) instead of ~13 + 4 shared-memory reads.  The 9 x 9 intermediate
+// values of the tile are built once per CTA from the low-resolution scores (16-byte loads along the class dimension)
+// into shared memory [pos][132] (row pitch = 4 mod 32 banks: the 8 cells x 4 groups of a warp hit 32 distinct banks).
+// Same interpolation formula and operand order as the generic kernels; the 4 partial winners of a pixel are merged
+// with "greater, or equal and lower class index" so the result is the first maximum, like argmax.
+constexpr int UQ_CELLS = 8, UQ_MID = UQ_CELLS + 1, UQ_PITCH = 132;
+__global__ void __launch_bounds__(256)
+upsample2x4_argmax_kernel(const float* __restrict__ lg, int64_t ldc, int64_t* __restrict__ labels, int h, int w, int ncls) {
+  pdl_sync();
+  __shared__ __align__(16) float mid[UQ_MID * UQ_MID * UQ_PITCH];
+  const int Hm = 2 * h, Wm = 2 * w, Ho = 8 * h, Wo = 8 * w;
+  const int b = blockIdx.z, cy0 = blockIdx.y * UQ_CELLS - 1, cx0 = blockIdx.x * UQ_CELLS - 1;   // first cell of the tile
+  const float* base = lg + static_cast<int64_t>(b) * h * w * ldc;
+  // ---- intermediate values (rows cy0 .. cy0 + 8, clamped = replicated at the borders), 4 classes per thread
+  const int nvec = (ncls + 3) / 4;                              // <= 32; the padded columns of a row are readable (ldc >= 4 nvec)
+  for (int i = threadIdx.x; i < UQ_MID * UQ_MID * 32; i += 256) {
+    const int c4 = i & 31, pos = i >> 5;
+    if (c4 >= nvec) continue;
+    const int my = min(max(cy0 + pos / UQ_MID, 0), Hm - 1), mx = min(max(cx0 + pos % UQ_MID, 0), Wm - 1);
+    const Lerp ly = lerp_coord(my, 0.5f, h), lx = lerp_coord(mx, 0.5f, w);
+    const float4 v00 = *reinterpret_cast<const float4*>(base + (static_cast<int64_t>(ly.i0) * w + lx.i0) * ldc + 4 * c4);
+    const float4 v01 = *reinterpret_cast<const float4*>(base + (static_cast<int64_t>(ly.i0) * w + lx.i1) * ldc + 4 * c4);
+    const float4 v10 = *reinterpret_cast<const float4*>(base + (static_cast<int64_t>(ly.i1) * w + lx.i0) * ldc + 4 * c4);
+    const float4 v11 = *reinterpret_cast<const float4*>(base + (static_cast<int64_t>(ly.i1) * w + lx.i1) * ldc + 4 * c4);
+    float4 m;
+    m.x = ly.w0 * (lx.w0 * v00.x + lx.w1 * v01.x) + ly.w1 * (lx.w0 * v10.x + lx.w1 * v11.x);
+    m.y = ly.w0 * (lx.w0 * v00.y + lx.w1 * v01.y) + ly.w1 * (lx.w0 * v10.y + lx.w1 * v11.y);
+    m.z = ly.w0 * (lx.w0 * v00.z + lx.w1 * v01.z) + ly.w1 * (lx.w0 * v10.z + lx.w1 * v11.z);
+    m.w = ly.w0 * (lx.w0 * v00.w + lx.w1 * v01.w) + ly.w1 * (lx.w0 * v10.w + lx.w1 * v11.w);
+    *reinterpret_cast<float4*>(mid + pos * UQ_PITCH + 4 * c4) = m;
+  }
+  __syncthreads();
+  // ---- thread = (cell, class group)
+  const int g = threadIdx.x & 3, cell = threadIdx.x >> 2, cxl = cell & (UQ_CELLS - 1), cyl = cell / UQ_CELLS;
+  const int Yb = 4 * (cy0 + cyl) + 2, Xb = 4 * (cx0 + cxl) + 2;  // first output pixel of the cell (may be -2)
+  float wy1[4], wx1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {                                 // out-of-range pixels are never stored; clamp for the weights
+    wy1[j] = lerp_coord(min(max(Yb + j, 0), Ho - 1), 0.25f, Hm).w1;
+    wx1[j] = lerp_coord(min(max(Xb + j, 0), Wo - 1), 0.25f, Wm).w1;
+  }
+  const float* p00 = mid + (cyl * UQ_MID + cxl) * UQ_PITCH + g;
+  const float* p01 = p00 + UQ_PITCH;
+  const float* p10 = p00 + UQ_MID * UQ_PITCH;
+  const float* p11 = p10 + UQ_PITCH;
+  float best[16];
+  int arg[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { best[k] = -INFINITY; arg[k] = 0; }
+  // lerp(a, b; w1) evaluated as a + w1 (b - a): one FMA per interpolated value (the generic kernels use
+  // w0 a + w1 b; the two differ by an ulp, which can only move an exact near-tie of the arg max)
+#pragma unroll 2
+  for (int c = g; c < ncls; c += 4) {
+    const float a = p00[c - g], bq = p01[c - g], cq = p10[c - g], d = p11[c - g];
+    const float dab = bq - a, dcd = d - cq;
+    float top[4], dtb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      top[j] = fmaf(wx1[j], dab, a);
+      dtb[j] = fmaf(wx1[j], dcd, cq) - top[j];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = fmaf(wy1[r], dtb[j], top[j]);
+        if (v > best[4 * r + j]) { best[4 * r + j] = v; arg[4 * r + j] = c; }
+      }
+  }
+  // ---- merge the 4 class groups (adjacent lanes); every lane ends with the winner
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best[k], o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg[k], o);
+      if (ov > best[k] || (ov == best[k] && oa < arg[k])) { best[k] = ov; arg[k] = oa; }
+    }
+  }
+  // lane g stores row g of the 4 x 4 block
+  int rowv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) rowv[j] = g == 0 ? arg[j] : (g == 1 ? arg[4 + j] : (g == 2 ? arg[8 + j] : arg[12 + j]));
+  const int Y = Yb + g;
+  if (Y >= 0 && Y < Ho) {
+    int64_t* orow = labels + (static_cast<int64_t>(b) * Ho + Y) * Wo;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int X = Xb + j;
+      if (X >= 0 && X < Wo) orow[X] = rowv[j];
+    }
+  }
+}
+
 inline int grid_for(int64_t work_items, int per_block = 256) {
   int64_t g = (work_items + per_block - 1) / per_block;
   const int64_t cap = 148 * 16;                               // grid-stride: a few waves over 148 SMs
@@ -656,9 +925,33 @@ extern "C" int cffm_dwconv3x3_gelu(const void* x, const void* w, const float* bi
   CFFM_REQUIRE(x && w && bias && out, CFFM_E_BADARG, "dwconv: null pointer");
   CFFM_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, CFFM_E_UNSUPPORTED, "dwconv: need C %% 8 == 0");
   CFFM_REQUIRE(aligned16(x) && aligned16(w) && aligned16(bias) && aligned16(out), CFFM_E_BADARG, "dwconv: misaligned");
-  launch_k(dwconv3x3_gelu_kernel, grid_for(static_cast<int64_t>(N) * H * ((W + DW_PX - 1) / DW_PX) * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream), 
-      static_cast<const __half*>(x), static_cast<const __half*>(w), bias, static_cast<__half*>(out), N, H, W, C);
-  return launch_status("dwconv3x3_gelu_kernel");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __half* xp = static_cast<const __half*>(x);
+  const __half* wp = static_cast<const __half*>(w);
+  __half* op = static_cast<__half*>(out);
+#define CFFM_DW_CT(CPT, PXW, RS, CT)                                                                                \
+  launch_k(dwconv3x3_gelu_rows_kernel<CPT, PXW, RS, CT>, static_cast<int>((threads + 255) / 256), 256, 0, st, xp, wp,   \
+           bias, op, N, H, W, C, sx, sy)
+#define CFFM_DW(CPT, PXW, RS)                                                                                       \
+  do {                                                                                                              \
+    const int sx = (W + PXW - 1) / PXW, sy = (H + RS - 1) / RS;                                                     \
+    const int64_t threads = static_cast<int64_t>(N) * sy * sx * (C / CPT);                                          \
+    CFFM_REQUIRE(threads < (1ll << 31), CFFM_E_UNSUPPORTED, "dwconv: tensor too large for 32-bit indexing");       \
+    switch (C) {                           /* hidden widths of MiT-B0 .. B5; anything else: run-time channel count */ \
+      case 128: CFFM_DW_CT(CPT, PXW, RS, 128); break;                                                               \
+      case 256: CFFM_DW_CT(CPT, PXW, RS, 256); break;                                                               \
+      case 512: CFFM_DW_CT(CPT, PXW, RS, 512); break;                                                               \
+      case 640: CFFM_DW_CT(CPT, PXW, RS, 640); break;                                                               \
+      case 1024: CFFM_DW_CT(CPT, PXW, RS, 1024); break;                                                             \
+      case 1280: CFFM_DW_CT(CPT, PXW, RS, 1280); break;                                                             \
+      case 2048: CFFM_DW_CT(CPT, PXW, RS, 2048); break;                                                             \
+      default: CFFM_DW_CT(CPT, PXW, RS, 0); break;                                                                  \
+    }                                                                                                               \
+  } while (0)
+  CFFM_DW(4, 4, 4);   // 4 channels x 4 x 4 pixels per thread: best of the measured (CPT, PXW, RS) on all four stage shapes
+#undef CFFM_DW
+#undef CFFM_DW_CT
+  return launch_status("dwconv3x3_gelu_rows_kernel");
 }
 
 extern "C" int cffm_head_fuse(const void* p1, const void* p2, const void* p3, const void* p4, int N, int H1, int W1,
@@ -672,7 +965,19 @@ extern "C" int cffm_head_fuse(const void* p1, const void* p2, const void* p3, co
   CFFM_REQUIRE(C % 64 == 0 && H1 % 2 == 0 && W1 % 2 == 0, CFFM_E_UNSUPPORTED, "head_fuse: need C %% 64 == 0 and even H1, W1");
   CFFM_REQUIRE((!c_half_f32 || ldh32 % 4 == 0) && (!c_half_f16 || ldh16 % 8 == 0), CFFM_E_BADARG, "head_fuse: bad stride");
   CFFM_REQUIRE(T_perm >= 0 && (T_perm <= 1 || N % T_perm == 0), CFFM_E_BADARG, "head_fuse: N=%d not a multiple of T_perm=%d", N, T_perm);
-  launch_k(head_fuse_kernel, grid_for(static_cast<int64_t>(N) * (H1 / 2) * (W1 / 2) * (C / 64) * 32), 256, 0, static_cast<cudaStream_t>(stream), 
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t warps = static_cast<int64_t>(N) * (H1 / 2) * (W1 / 2) * (C / 64);
+  CFFM_REQUIRE(warps * 32 < (1ll << 31), CFFM_E_UNSUPPORTED, "head_fuse: tensor too large for 32-bit indexing");
+  const bool pyramid = H1 % 8 == 0 && W1 % 8 == 0 && H2 * 2 == H1 && W2 * 2 == W1 && H3 * 4 == H1 && W3 * 4 == W1 &&
+                       H4 * 8 == H1 && W4 * 8 == W1;
+  if (pyramid) {
+    const int64_t threads = static_cast<int64_t>(N) * (H1 / 2) * (W1 / 2) * (C / 8);
+    launch_k(head_fuse_pyramid_kernel, static_cast<int>((threads + 255) / 256), 256, 0, st, static_cast<const __half*>(p1),
+             static_cast<const __half*>(p2), static_cast<const __half*>(p3), static_cast<const __half*>(p4), N, H1, W1, C, T_perm,
+             shift, static_cast<__half*>(c_full), c_half_f32, ldh32, static_cast<__half*>(c_half_f16), ldh16);
+    return launch_status("head_fuse_pyramid_kernel");
+  }
+  launch_k(head_fuse_kernel, grid_for(warps * 32), 256, 0, st,
       static_cast<const __half*>(p1), static_cast<const __half*>(p2), static_cast<const __half*>(p3),
       static_cast<const __half*>(p4), N, H1, W1, H2, W2, H3, W3, H4, W4, C, T_perm, shift, static_cast<__half*>(c_full),
       c_half_f32, ldh32, static_cast<__half*>(c_half_f16), ldh16);
@@ -770,6 +1075,13 @@ extern "C" int cffm_upsample2_argmax(const float* scores, int64_t ldc, int64_t* 
   CFFM_REQUIRE(scores && labels, CFFM_E_BADARG, "upsample2_argmax: null pointer");
   CFFM_REQUIRE(B > 0 && h > 0 && w > 0 && ncls > 0 && Hm > 0 && Wm > 0 && Ho > 0 && Wo > 0 && ldc >= ncls && B <= 65535,
                CFFM_E_BADARG, "upsample2_argmax: bad size");
+  if (Hm == 2 * h && Wm == 2 * w && Ho == 4 * Hm && Wo == 4 * Wm && ncls <= 128 && ldc % 4 == 0 && ldc >= (ncls + 3) / 4 * 4 &&
+      aligned16(scores)) {
+    // cells cy = -1 .. Hm - 1 (the first / last ones are half outside the image)
+    dim3 grid((Wm + 1 + UQ_CELLS - 1) / UQ_CELLS, (Hm + 1 + UQ_CELLS - 1) / UQ_CELLS, B);
+    launch_k(upsample2x4_argmax_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), scores, ldc, labels, h, w, ncls);
+    return launch_status("upsample2x4_argmax_kernel");
+  }
   // intermediate rows/cols touched by a 16-pixel output tile: 16 * Hm/Ho + 3 (two taps + rounding)
   const int need_y = (UP_TILE * Hm + Ho - 1) / Ho + 3, need_x = (UP_TILE * Wm + Wo - 1) / Wo + 3;
   CFFM_REQUIRE(need_y <= UP_MT && need_x <= UP_MT, CFFM_E_UNSUPPORTED,

@@ -9,7 +9,7 @@ from . import _abi
 
 
 class GraphedClips:
-    def __init__(self, model, B, T, H, W, img_meta=None, rescale=True, head_kw=None, warmup=3):
+    def __init__(self, model, B, T, H, W, img_meta=None, rescale=True, head_kw=None, warmup=3, private_input=False):
         dev = model._device()
         if dev.type != "cuda":
             raise _abi.CffmError("CUDA graphs need the model on a CUDA device")
@@ -17,7 +17,10 @@ class GraphedClips:
         self.meta = img_meta or [dict(ori_shape=(H, W, 3), img_shape=(H, W, 3), pad_shape=(H, W, 3), flip=False,
                                       filename="data/video/origin/00000000.jpg") for _ in range(B)]
         head_kw = dict(head_kw or {})
-        self.frames = model._ws.get("frames", (T, B, 3, H, W), torch.float32, device=dev)   # static input buffer
+        if private_input:                                        # pipeline slots: one static input buffer per graph
+            self.frames = torch.empty(T, B, 3, H, W, dtype=torch.float32, device=dev)
+        else:
+            self.frames = model._ws.get("frames", (T, B, 3, H, W), torch.float32, device=dev)   # static input buffer
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                            # plans, workspaces, func attributes: all set here
@@ -46,3 +49,70 @@ class GraphedClips:
     def __call__(self, imgs):
         self.load(imgs)
         return self.replay()
+
+
+class ClipPipeline:
+    """Streaming inference from HOST buffers: the H2D copy of clip batch i+1 and the D2H read of the labels of
+    batch i-1 overlap the kernels of batch i.  ``depth`` graph instances (one static input buffer and one label
+    buffer each, shared workspace) rotate; three streams (copy-in, compute, copy-out) are ordered with events only,
+    so ``submit`` never blocks the host unless all slots are in flight.
+
+        pipe = ClipPipeline(model, B, T, H, W)
+        tickets = [pipe.submit(frames_host[i], labels_host[i]) for i in ...]   # pinned host tensors
+        pipe.wait(tickets[-1])                                                   # or pipe.drain()
+    """
+
+    def __init__(self, model, B, T, H, W, img_meta=None, rescale=True, head_kw=None, depth=2):
+        dev = model._device()
+        self.dev, self.depth, self.T = dev, depth, T
+        self.slots = []
+        for s in range(depth):
+            g = GraphedClips(model, B, T, H, W, img_meta, rescale, head_kw, warmup=3 if s == 0 else 1, private_input=True)
+            self.slots.append(dict(g=g, h2d=torch.cuda.Event(), done=torch.cuda.Event(), d2h=torch.cuda.Event(), used=False))
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self.n = 0
+
+    @property
+    def compute_stream(self):
+        return self.s_run
+
+    def submit(self, imgs, labels_host):
+        """imgs: list of T (B,3,H,W) pinned host tensors (or one (T,B,3,H,W)); labels_host: pinned int64 (B,H,W)."""
+        sl = self.slots[self.n % self.depth]
+        g = sl["g"]
+        with torch.cuda.stream(self.s_in):
+            if sl["used"]:
+                self.s_in.wait_event(sl["done"])                 # the previous batch in this slot has been consumed
+            if isinstance(imgs, (list, tuple)):
+                for t, f in enumerate(imgs):
+                    g.frames[t].copy_(f, non_blocking=True)
+            else:
+                g.frames.copy_(imgs, non_blocking=True)
+            sl["h2d"].record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(sl["h2d"])
+            if sl["used"]:
+                self.s_run.wait_event(sl["d2h"])                 # its label buffer has been read back
+            g.replay()
+            sl["done"].record(self.s_run)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(sl["done"])
+            labels_host.copy_(g.labels, non_blocking=True)
+            sl["d2h"].record(self.s_out)
+        sl["used"] = True
+        self.n += 1
+        return sl["d2h"]
+
+    @staticmethod
+    def wait(ticket):
+        ticket.synchronize()
+
+    def drain(self):
+        for sl in self.slots:
+            if sl["used"]:
+                sl["d2h"].synchronize()
+
+    @property
+    def kernels_per_step(self):
+        return self.slots[0]["g"].kernels_per_replay
+
