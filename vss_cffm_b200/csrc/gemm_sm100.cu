@@ -28,7 +28,8 @@ constexpr int NUM_EPI_WARPS = 16;                 // four per TMEM lane quarter;
 constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int STG_LD = 36;                        // padded fp32 row of the per-warp 32x32 transpose buffer
-constexpr int STG_BYTES = 32 * STG_LD * 4 + 128;   // 32x36 fp32 transpose buffer (or 32 x 80 B fp16 rows) + 32-float bias slice
+constexpr int STG_BYTES = 5120;                   // per epilogue warp, 512-byte aligned: 32x36 fp32 transpose buffer, or a 32 x 64 B
+                                                  // swizzled fp16 tile (TMA store source); the last 128 bytes hold a 32-float bias slice
 
 struct Epilogue {
   const float* bias;
@@ -78,7 +79,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 template <int BN, bool F16_ONLY, bool LN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                    const Epilogue ep, const int M, const int N, const int K, const int n_tiles_n,
+                    const __grid_constant__ CUtensorMap tmO, const Epilogue ep, const int M, const int N, const int K, const int n_tiles_n,
                     const int n_tiles) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -104,6 +105,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmW);
+    if (F16_ONLY) ptx::prefetch_tensormap(&tmO);
     for (int s = 0; s < C::STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -212,9 +214,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);     // registers hold the chunk: MMA may reuse the stage
         if (dbg & 2) continue;                                 // probe: no epilogue work at all
-        // bias + activation in the thread = row layout (bias is warp-uniform: broadcast LDS), pack to fp16 and
-        // stage [32 rows][64 B]; then 4 lanes write one row chunk (64 contiguous bytes), 8 rows per instruction.
-        constexpr int P16 = 80;                                // padded row pitch (bytes): conflict-free STS.128
+        // bias + activation in the thread = row layout (bias is warp-uniform: broadcast LDS), pack to fp16 and stage the
+        // warp's 32 x 32 chunk as [32 rows][64 B] in the 64-byte TMA swizzle (16-byte piece j of row r sits at
+        // j ^ ((r >> 1) & 3): the 8 lanes of a store phase hit 8 distinct 16-byte bank groups).  One lane then hands the
+        // tile to the TMA unit: a single bulk tensor store replaces the shared-memory read-back and the predicated
+        // global stores (the L1/LSU pipe was the busiest unit of this kernel), and clips the M / N tails in hardware.
+        if (lane == 0) ptx::bulk_wait_read0();                 // the previous tile's store has drained this buffer
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 b0 = *reinterpret_cast<const float4*>(sbias + 8 * j);
@@ -227,22 +233,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int e = 0; e < 8; ++e) a[e] = apply_act(a[e], act);
           }
-          *reinterpret_cast<uint4*>(stg8 + lane * P16 + 16 * j) =
+          *reinterpret_cast<uint4*>(stg8 + lane * 64 + 16 * (j ^ ((lane >> 1) & 3))) =
               make_uint4(pack_half2(a[0], a[1]), pack_half2(a[2], a[3]), pack_half2(a[4], a[5]), pack_half2(a[6], a[7]));
         }
+        ptx::fence_proxy_async();                              // generic-proxy writes -> visible to the TMA (async proxy)
         __syncwarp();
-        const int piece = lane & 3, rr = lane >> 2;
-        const int col = wcol0 + 8 * piece;
-        if (col < N && !(dbg & 1)) {
-          __half* obase = ep.out16 + static_cast<int64_t>(wrow0 + rr) * ep.ldo16 + col;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = wrow0 + rr + 8 * i;
-            const uint4 val = *reinterpret_cast<const uint4*>(stg8 + (rr + 8 * i) * P16 + 16 * piece);
-            if (row < M) *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(8 * i) * ep.ldo16) = val;
-          }
+        if (lane == 0 && wcol0 < N && wrow0 < M && !(dbg & 1)) {
+          ptx::tma_store_2d(&tmO, stg8, wcol0, wrow0);
+          ptx::bulk_commit();
         }
-        __syncwarp();                                          // staging buffer is re-used by the next tile
         continue;
       }
       // ---- general path: fp32 and/or fp16 output, optional fp32 residual (may alias out32), optional LayerNorm
@@ -360,6 +359,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   }
+  if (F16_ONLY && warp >= 2 && lane == 0) ptx::bulk_wait_read0();   // shared memory must outlive the bulk stores reading it
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -457,6 +457,22 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t K, int64_
   return CFFM_OK;
 }
 
+// fp16 [rows, cols] output (row stride ld elements) as the target of per-warp 32 x 32 bulk stores (64-byte swizzle).
+static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  CFFM_REQUIRE(fn != nullptr, CFFM_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CFFM_REQUIRE(r == CUDA_SUCCESS, CFFM_E_DRIVER, "cuTensorMapEncodeTiled (output) failed with CUresult %d (rows=%lld cols=%lld ld=%lld)",
+               static_cast<int>(r), (long long)rows, (long long)cols, (long long)ld);
+  return CFFM_OK;
+}
+
 namespace {
 
 template <int BN, bool F16_ONLY, bool LN = false>
@@ -467,6 +483,11 @@ int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const
   if (rc) return rc;
   rc = make_tmap(&tmW, W, N, K, ldw, BN);
   if (rc) return rc;
+  CUtensorMap tmO = tmA;                                       // only read by the fp16-only epilogue
+  if (F16_ONLY) {
+    rc = make_tmap_out(&tmO, ep.out16, M, N, ep.ldo16);
+    if (rc) return rc;
+  }
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -477,7 +498,7 @@ int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
   const int tiles = tiles_n * tiles_m * ep.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  launch_k(gemm_tcgen05_kernel<BN, F16_ONLY, LN>, grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st, tmA, tmW, ep, M, N, K, tiles_n, tiles);
+  launch_k(gemm_tcgen05_kernel<BN, F16_ONLY, LN>, grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st, tmA, tmW, tmO, ep, M, N, K, tiles_n, tiles);
   return launch_status("gemm_tcgen05_kernel");
 }
 
