@@ -93,6 +93,13 @@ int cffm_layernorm_sum(const float* partials, int nsum, const float* bias, const
                        const float* beta, float eps, void* out_f16, int64_t ldo16, float* out_f32,
                        int64_t ldo32, int M, int C, void* stream);
 
+/* Two chained LayerNorms in one pass: y = LayerNorm(sum_s partials[s] + bias; gamma, beta, eps) -> out_f32 [M,C];
+ * LayerNorm(y; gamma2, beta2, eps2) -> out_f16 [M,C].  OverlapPatchEmbed.norm followed by the first block's norm1
+ * (mix_transformer.py:198 then :154).  partials fp32 [nsum, M, C] contiguous; bias may be NULL. */
+int cffm_layernorm_chain(const float* partials, int nsum, const float* bias, const float* gamma, const float* beta,
+                         float eps, float* out_f32, int64_t ldo32, const float* gamma2, const float* beta2,
+                         float eps2, void* out_f16, int64_t ldo16, int M, int C, void* stream);
+
 /* Row LayerNorm over C channels, fp32 statistics.  x is fp32 (x_is_f32=1) or fp16.
  * Writes fp16 and/or fp32.  mix_transformer.py:154-155,198,321  cffm_transformer.py:824
  * swin_transformer_2d.py:619,622,663. */
@@ -155,6 +162,13 @@ int cffm_cffa_norm_frames(const float* x, const float* gamma, const float* beta,
  * [49+49+9+4], pool_b fp32 [4].  cffm_transformer.py:739-805. */
 int cffm_cffa_pool(const void* xn, int B, int T, int H, int W, int C, const float* pool_w,
                    const float* pool_b, void* pooled, void* stream);
+
+/* The same pooling split in two, writing DISJOINT rows of the same pooled [B, P, C] buffer, so that the
+ * reference-frame levels (which never change while the blocks update the target) can be produced ahead of
+ * time on another stream.  part 0: the target level only, xn fp16 [B,H,W,C] = the LN'ed target frames;
+ * part 1: the three reference levels only, xn fp16 [3,B,H,W,C] = the LN'ed reference frames, frame-major. */
+int cffm_cffa_pool_part(const void* xn, int B, int part, int H, int W, int C, const float* pool_w,
+                        const float* pool_b, void* pooled, void* stream);
 
 /* One pooling level of n independent LN'ed frames xn fp16 [n,H,W,C] (frame-sharded multi-GPU path: the
  * owner of a reference frame pools it for its temporal role).  level 0: target 7x7 | 1: ref0 7x7 |

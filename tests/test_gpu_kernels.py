@@ -121,6 +121,24 @@ def test_layernorm(ops, M, C, f32in):
         check(o16, ref, REL16, "layernorm f16")
 
 
+@pytest.mark.parametrize("S,M,C", [(1, 1000, 64), (4, 300, 320), (8, 77, 512), (2, 129, 128), (1, 9, 32)])
+def test_layernorm_chain(ops, S, M, C):
+    """LN(sum of split-K partials + bias) -> fp32, then LN2 of that -> fp16 (patch-embed norm + first norm1)."""
+    parts = synth.synth_array((S, M, C), 11, scale=2.0)
+    bias = synth.synth_array((C,), 12)
+    g1, b1 = synth.synth_array((C,), 13) * 0.1 + 1, synth.synth_array((C,), 14) * 0.1
+    g2, b2 = synth.synth_array((C,), 15) * 0.1 + 1, synth.synth_array((C,), 16) * 0.1
+    y = F.layer_norm(parts.double().sum(0) + bias.double(), (C,), g1.double(), b1.double(), 1e-5)
+    z = F.layer_norm(y, (C,), g2.double(), b2.double(), 1e-6)
+    o32 = torch.empty(M, C, dtype=torch.float32, device="cuda")
+    o16 = torch.empty(M, C, dtype=torch.float16, device="cuda")
+    ops.layernorm_chain(parts.cuda(), bias.cuda(), g1.cuda(), b1.cuda(), 1e-5, o32, g2.cuda(), b2.cuda(), 1e-6, o16)
+    check(o32, y, REL32, "chain: first norm")
+    check(o16, z, REL16, "chain: second norm")
+    ops.layernorm_chain(parts[:1].contiguous().cuda(), None, g1.cuda(), b1.cuda(), 1e-5, o32, g2.cuda(), b2.cuda(), 1e-6, o16)
+    check(o32, F.layer_norm(parts[0].double(), (C,), g1.double(), b1.double(), 1e-5), REL32, "chain: no bias")
+
+
 @pytest.mark.parametrize("layout,N,H,W,C,k,s,p", [(0, 2, 64, 96, 3, 7, 4, 3), (1, 2, 16, 24, 64, 3, 2, 1),
                                                   (1, 1, 16, 24, 32, 8, 8, 0), (1, 3, 9, 7, 160, 3, 2, 1),
                                                   (1, 2, 8, 12, 128, 4, 4, 0)])
@@ -255,6 +273,13 @@ def test_cffa_norm_and_pool_vs_oracle(ops, B, H, W):
         check(got[:, off:off + n], pr.reshape(B, n, C), REL16, f"pooled level {lvl}")
         off += n
     assert off == 15 * nW
+    # the two-part form used by the head (reference levels ahead of time, target level per block) fills the same buffer
+    split = torch.full_like(pooled, float("nan"))
+    xn5 = xn.view(T, B, H, W, C)
+    ops.cffa_pool_part(xn5[:T - 1].contiguous(), B, 1, H, W, C, pw, pb, split)
+    assert torch.isnan(split.view(B, 15 * nW, C)[:, :nW]).all()                  # target rows untouched by the reference part
+    ops.cffa_pool_part(xn5[T - 1].contiguous(), B, 0, H, W, C, pw, pb, split)
+    assert torch.equal(split, pooled)                                             # bit-identical to the one-pass kernel
 
 
 # ------------------------------------------------------------------------------------ CFM attention

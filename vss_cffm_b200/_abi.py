@@ -32,6 +32,7 @@ SIGNATURES = {
     "cffm_gemm_f16_splitk": ([vp, i64, vp, i64, vp, i32, i32, i32, i32, vp], i32),
     "cffm_splitk_plan": ([i32, i32, i32], i32),
     "cffm_layernorm_sum": ([vp, i32, vp, vp, vp, f32, vp, i64, vp, i64, i32, i32, vp], i32),
+    "cffm_layernorm_chain": ([vp, i32, vp, vp, vp, f32, vp, i64, vp, vp, f32, vp, i64, i32, i32, vp], i32),
     "cffm_layernorm": ([vp, i32, i64, vp, vp, f32, vp, i64, vp, i64, i32, i32, vp], i32),
     "cffm_im2col": ([vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp], i32),
     "cffm_mha_f16": ([vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, f32, vp], i32),
@@ -41,6 +42,7 @@ SIGNATURES = {
     "cffm_cffa_norm": ([vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp], i32),
     "cffm_cffa_norm_frames": ([vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp], i32),
     "cffm_cffa_pool": ([vp, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
+    "cffm_cffa_pool_part": ([vp, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
     "cffm_cffa_pool_level": ([vp, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
     "cffm_cfm_attention": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),
     "cffm_cfm_key_sources": ([i32, i32, vp, vp], i32),

@@ -231,6 +231,7 @@ class CFFMHead_clips_resize1_8(BaseDecodeHead_clips_flow):
             self.finetune = True
         self._plan = None
         self._ws = Workspace()
+        self._early, self._early_src = {}, None                  # projections started by project_stage(), and their owner
         self.training = False
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_plan())
 
@@ -355,6 +356,28 @@ class CFFMHead_clips_resize1_8(BaseDecodeHead_clips_flow):
         ops.resize_nhwc_to_nchw(lg, self.num_classes, out, batch_size, hs, ws_, h, w)    # (:149); identity when early
         return out
 
+    def project_stage(self, i, feat):
+        """Folded ``linear_c{i+1}`` projection of ONE backbone stage (cffm_head.py:108-117), enqueued on a side stream
+        the moment that stage exists: it then overlaps the later backbone stages, which leave most SMs idle.
+        ``forward_scores`` picks the result up if it is handed the very same feature map."""
+        if feat.device.type != "cuda":
+            return
+        P = self._plan or self._build_plan()
+        if i not in self.in_index:
+            return
+        slot = list(self.in_index).index(i)
+        t = self._as_nhwc16(feat)
+        n, h, w, c = t.shape
+        out = self._ws.get(f"p{slot}", (n * h * w, self.embed_dim), _H)
+        with ops.fork("proj"):
+            ops.gemm(t.reshape(-1, c), P["pw"][slot], out16=out)
+        self._early[slot] = (t.data_ptr(), tuple(t.shape), out)
+
+    def early_projections_belong_to(self, feature_list):
+        """The caller of ``project_stage`` names the list of feature maps the projections were computed from;
+        ``forward_scores`` re-uses them only when it is handed that very list object (anything else recomputes)."""
+        self._early_src = feature_list
+
     def forward_scores(self, inputs, batch_size, num_clips, img_metas=None, *, centers=None, frame_major=False):
         """Everything of ``forward`` up to (not including) the last bilinear resize: class scores of the target
         frames, NHWC fp32 ``[B*hs*ws, ncp]`` (first num_classes columns valid), their size (hs, ws) and the size
@@ -375,11 +398,19 @@ class CFFMHead_clips_resize1_8(BaseDecodeHead_clips_flow):
         t_perm = 0 if (frame_major or T == 1) else T
         # ---- per-frame MLP decoder, folded (:108-119)
         proj = [ws.get(f"p{i}", (N * sizes[i][0] * sizes[i][1], E), _H) for i in range(4)]
-        with ops.fork():                                         # the three small projections beside the big one
-            for i in (1, 2, 3):
-                ops.gemm(feats[i].reshape(-1, feats[i].shape[3]), P["pw"][i], out16=proj[i])
-        ops.gemm(feats[0].reshape(-1, feats[0].shape[3]), P["pw"][0], out16=proj[0])
-        ops.join()
+        owned = inputs is self._early_src and self._early_src is not None
+        early_done = {i for i, (ptr, shp, buf) in self._early.items()
+                      if owned and ptr == feats[i].data_ptr() and shp == tuple(feats[i].shape) and buf.data_ptr() == proj[i].data_ptr()}
+        if self._early:
+            ops.join("proj")                                     # whatever project_stage() started must finish before p{i} is re-used
+        self._early, self._early_src = {}, None
+        todo = [i for i in range(4) if i not in early_done]
+        if todo:
+            with ops.fork():                                     # the small projections beside the big one
+                for i in todo[1:]:
+                    ops.gemm(feats[i].reshape(-1, feats[i].shape[3]), P["pw"][i], out16=proj[i])
+            ops.gemm(feats[todo[0]].reshape(-1, feats[todo[0]].shape[3]), P["pw"][todo[0]], out16=proj[todo[0]])
+            ops.join()
         early = num_clips != self.num_clips                      # eval-mode early return (:127-129)
         if early:
             c_full = ws.get("c_full", (N * h * w, E), _H)
@@ -409,27 +440,45 @@ class CFFMHead_clips_resize1_8(BaseDecodeHead_clips_flow):
         Hp, Wp = _round_up(h2, WS), _round_up(w2, WS)
         nW = (Hp // WS) * (Wp // WS)
         Pp = 15 * nW
-        xn = ws.get("xn", (N * HW, E), _H)
+        nref = (T - 1) * B                                       # frame-major: reference frames first, targets last
+        xn_t = ws.get("xn_t", (B * HW, E), _H)
         xt_pad = ws.get("xt_pad", (B * Hp * Wp, E), _H, zero=True)     # pad rows stay zero (pad AFTER norm, :716-724)
-        pooled = ws.get("pooled", (B * Pp, E), _H)
         qkv_t = ws.get("qkv_t", (B * Hp * Wp, 3 * E), _H)
-        kvp = ws.get("kvp", (B * Pp, 2 * E), _H)
         ao = ws.get("ao", (B * HW, E), _H)
         xn2 = ws.get("xn2", (B * HW, E), _H)
         hid = ws.get("hid", (B * HW, 4 * E), _H)
         xt16 = ws.get("xt16", (B * HW, E), _H)
+        depth = len(P["blocks"])
+
+        def assemble_refs(i):
+            """Reference-frame side of CFFA for block i (norm1 -> pad -> resize -> fc-pool, :713-805).  A block never
+            modifies the reference frames (:826), so this does not depend on the previous block: it runs on its own
+            stream beside the target path and is joined just before the pooled K/V projection."""
+            b = P["blocks"][i]
+            xn_r = ws.get(f"xn_r{i}", (nref * HW, E), _H)
+            pooled = ws.get(f"pooled{i}", (B * Pp, E), _H)
+            with ops.fork("refs"):
+                ops.cffa_norm_frames(x32[:nref * HW], b["n1g"], b["n1b"], b["n1eps"], xn_r, None, nref, nref, h2, w2, Hp, Wp, E)
+                ops.cffa_pool_part(xn_r, B, 1, h2, w2, E, b["pool_w"], b["pool_b"], pooled)
+
+        assemble_refs(0)
         for i, b in enumerate(P["blocks"]):
-            ops.cffa_norm(x32, b["n1g"], b["n1b"], b["n1eps"], xn, xt_pad, B, T, h2, w2, Hp, Wp, E)
-            with ops.fork():                                     # pooling + its K/V projection beside the target QKV
-                ops.cffa_pool(xn, B, T, h2, w2, E, b["pool_w"], b["pool_b"], pooled)
+            pooled = ws.get(f"pooled{i}", (B * Pp, E), _H)
+            kvp = ws.get(f"kvp{i}", (B * Pp, 2 * E), _H)
+            ops.cffa_norm_frames(xt, b["n1g"], b["n1b"], b["n1eps"], xn_t, xt_pad, B, 0, h2, w2, Hp, Wp, E)
+            with ops.fork():                                     # target-level pooling + pooled K/V projection beside the target QKV
+                ops.cffa_pool_part(xn_t, B, 0, h2, w2, E, b["pool_w"], b["pool_b"], pooled)
+                ops.join("refs")                                 # reference levels of this block (started one block earlier)
                 ops.gemm(pooled, b["qkv_w"][E:], bias=b["qkv_b"][E:], out16=kvp)   # Q third is dead work (:449)
+            if i + 1 < depth:
+                assemble_refs(i + 1)
             ops.gemm(xt_pad, b["qkv_w"], bias=b["qkv_b"], out16=qkv_t)
             ops.join()
             ops.cfm_attention(qkv_t, kvp, b["bias"], ao, B, h2, w2, E, HEADS_N, (E // HEADS_N) ** -0.5)
             ops.gemm(ao, b["proj_w"], bias=b["proj_b"], residual=xt, out32=xt)
             ops.layernorm(xt, b["n2g"], b["n2b"], b["n2eps"], out16=xn2)
             ops.gemm(xn2, b["f1w"], bias=b["f1b"], out16=hid, act=ops.ACT_GELU)
-            last = i == len(P["blocks"]) - 1
+            last = i == depth - 1
             ops.gemm(hid, b["f2w"], bias=b["f2b"], residual=xt, out32=xt, out16=xt16 if last else None)
         # ---- linear_pred2 on cat([_c_further[:,-1], _c2[:,-1]]) without the concat (:145-148)
         lg = ws.get("lg", (B * HW, ncp), _F)

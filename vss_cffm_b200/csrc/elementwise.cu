@@ -31,7 +31,10 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ xin, int64_t ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ o16, int64_t ldo16,
                  float* __restrict__ o32, int64_t ldo32, int M, int C, int nsum, int64_t sum_stride,
-                 const float* __restrict__ sum_bias) {
+                 const float* __restrict__ sum_bias, const float* __restrict__ gamma2 = nullptr,
+                 const float* __restrict__ beta2 = nullptr, float eps2 = 0.f) {
+  // gamma2 != nullptr: two chained LayerNorms in one pass -- o32 receives y = LN(x), o16 receives LN2(y)
+  // (patch-embed norm followed by the first block's norm1: the row never leaves the registers in between)
   pdl_sync();
   constexpr int RPW = 32 / L;                                  // rows per warp
   const int lane = threadIdx.x & 31;
@@ -91,18 +94,57 @@ layernorm_kernel(const void* __restrict__ xin, int64_t ldx, const float* __restr
 #pragma unroll
     for (int o = L / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq * invC + eps);
+    if (gamma2 == nullptr) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = gl + i * L;
-      if (rv && v < nvec) {
-        float4 y;
-        y.x = x[i].x * rstd * g[i].x + b[i].x; y.y = x[i].y * rstd * g[i].y + b[i].y;
-        y.z = x[i].z * rstd * g[i].z + b[i].z; y.w = x[i].w * rstd * g[i].w + b[i].w;
-        if (o32) *reinterpret_cast<float4*>(o32 + row * ldo32 + 4 * v) = y;
-        if (o16) {
+      for (int i = 0; i < NV; ++i) {
+        const int v = gl + i * L;
+        if (rv && v < nvec) {
+          float4 y;
+          y.x = x[i].x * rstd * g[i].x + b[i].x; y.y = x[i].y * rstd * g[i].y + b[i].y;
+          y.z = x[i].z * rstd * g[i].z + b[i].z; y.w = x[i].w * rstd * g[i].w + b[i].w;
+          if (o32) *reinterpret_cast<float4*>(o32 + row * ldo32 + 4 * v) = y;
+          if (o16) {
+            uint2 h;
+            h.x = pack_half2(y.x, y.y);
+            h.y = pack_half2(y.z, y.w);
+            *reinterpret_cast<uint2*>(o16 + row * ldo16 + 4 * v) = h;
+          }
+        }
+      }
+    } else {
+      float sum2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = gl + i * L;
+        if (v < nvec) {
+          x[i].x = x[i].x * rstd * g[i].x + b[i].x; x[i].y = x[i].y * rstd * g[i].y + b[i].y;
+          x[i].z = x[i].z * rstd * g[i].z + b[i].z; x[i].w = x[i].w * rstd * g[i].w + b[i].w;
+          if (rv && o32) *reinterpret_cast<float4*>(o32 + row * ldo32 + 4 * v) = x[i];
+          sum2 += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+        }
+      }
+#pragma unroll
+      for (int o = L / 2; o > 0; o >>= 1) sum2 += __shfl_xor_sync(0xffffffffu, sum2, o);
+      const float mean2 = sum2 * invC;
+      float sq2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (gl + i * L < nvec) {
+          x[i].x -= mean2; x[i].y -= mean2; x[i].z -= mean2; x[i].w -= mean2;
+          sq2 += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
+        }
+      }
+#pragma unroll
+      for (int o = L / 2; o > 0; o >>= 1) sq2 += __shfl_xor_sync(0xffffffffu, sq2, o);
+      const float rstd2 = rsqrtf(sq2 * invC + eps2);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = gl + i * L;
+        if (rv && v < nvec) {
+          const float4 g2 = *reinterpret_cast<const float4*>(gamma2 + 4 * v), b2 = *reinterpret_cast<const float4*>(beta2 + 4 * v);
           uint2 h;
-          h.x = pack_half2(y.x, y.y);
-          h.y = pack_half2(y.z, y.w);
+          h.x = pack_half2(x[i].x * rstd2 * g2.x + b2.x, x[i].y * rstd2 * g2.y + b2.y);
+          h.y = pack_half2(x[i].z * rstd2 * g2.z + b2.z, x[i].w * rstd2 * g2.w + b2.w);
           *reinterpret_cast<uint2*>(o16 + row * ldo16 + 4 * v) = h;
         }
       }
@@ -541,7 +583,9 @@ cffa_pool_kernel(const __half* __restrict__ xn, int B, int T, int H, int W, int 
   pdl_sync();
   constexpr int C = 256, WS = 7;
   const int nWh = Hp / WS, nWw = Wp / WS, nW = nWh * nWw;
-  // only_level < 0: all four levels of B clips from the frame-major stack xn [T,B,H,W,C] (P = 15 nW tokens per clip);
+  // only_level < 0: the levels of B clips from the frame-major stack xn [T,B,H,W,C] (P = 15 nW tokens per clip):
+  //   -1 all four; -2 the three reference levels only (xn = reference frames [3,B,...]); -3 the target level only
+  //   (xn = target frames [B,...], T = 1);  the rows of the other levels are left untouched
   // only_level = l: level l of B independent frames xn [B,H,W,C] (P = {1,1,4,9}[l] nW tokens per frame)
   const int P = only_level < 0 ? 15 * nW : (only_level < 2 ? nW : (only_level == 2 ? 4 * nW : 9 * nW));
   const int64_t gw = blockIdx.x * 8ll + (threadIdx.x >> 5);
@@ -555,6 +599,7 @@ cffa_pool_kernel(const __half* __restrict__ xn, int B, int T, int H, int W, int 
   else if (pos < 2 * nW) { level = 1; pos -= nW; }
   else if (pos < 6 * nW) { level = 2; pos -= 2 * nW; }
   else { level = 3; pos -= 6 * nW; }
+  if ((only_level == -2 && level == 0) || (only_level == -3 && level != 0)) return;
   if (level == 0) { frame = T - 1; wg = 7; gwid = nWw; woff = 0; }
   else if (level == 1) { frame = 0; wg = 7; gwid = nWw; woff = 49; }
   else if (level == 2) { frame = 1; wg = 3; gwid = 2 * nWw; woff = 98; }
@@ -857,14 +902,15 @@ using namespace cffm;
 template <bool F32, int L, int NV>
 static void launch_ln(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, __half* o16,
                       int64_t ldo16, float* o32, int64_t ldo32, int M, int C, cudaStream_t st, int nsum = 1,
-                      int64_t sum_stride = 0, const float* sum_bias = nullptr) {
+                      int64_t sum_stride = 0, const float* sum_bias = nullptr, const float* gamma2 = nullptr,
+                      const float* beta2 = nullptr, float eps2 = 0.f) {
   constexpr int RPW = 32 / L;
   const int64_t warps = (static_cast<int64_t>(M) + RPW - 1) / RPW;
   int64_t grid = (warps + 7) / 8;
   const int64_t cap = 148 * 8 * 4;                             // 8 resident CTAs per SM, a few rows per warp
   if (grid > cap) grid = cap;
   launch_k(layernorm_kernel<F32, L, NV>, static_cast<int>(grid), 256, 0, st, x, ldx, gamma, beta, eps, o16, ldo16, o32, ldo32, M, C,
-           nsum, sum_stride, sum_bias);
+           nsum, sum_stride, sum_bias, gamma2, beta2, eps2);
 }
 
 extern "C" int cffm_layernorm(const void* x, int x_is_f32, int64_t ldx, const float* gamma, const float* beta,
@@ -1022,6 +1068,19 @@ extern "C" int cffm_cffa_pool(const void* xn, int B, int T, int H, int W, int C,
   return launch_status("cffa_pool_kernel");
 }
 
+extern "C" int cffm_cffa_pool_part(const void* xn, int B, int part, int H, int W, int C, const float* pool_w,
+                                   const float* pool_b, void* pooled, void* stream) {
+  CFFM_REQUIRE(xn && pool_w && pool_b && pooled, CFFM_E_BADARG, "cffa_pool_part: null pointer");
+  CFFM_REQUIRE(B > 0 && H > 0 && W > 0 && (part == 0 || part == 1), CFFM_E_BADARG, "cffa_pool_part: bad size/part");
+  CFFM_REQUIRE(C == 256, CFFM_E_UNSUPPORTED, "cffa_pool_part: built for C=256, got %d", C);
+  const int Hp = (H + 6) / 7 * 7, Wp = (W + 6) / 7 * 7;
+  const int64_t warps = static_cast<int64_t>(B) * 15 * (Hp / 7) * (Wp / 7);
+  launch_k(cffa_pool_kernel, static_cast<int>((warps + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream),
+           static_cast<const __half*>(xn), B, part == 0 ? 1 : 4, H, W, Hp, Wp, pool_w, pool_b, static_cast<__half*>(pooled),
+           part == 0 ? -3 : -2);
+  return launch_status("cffa_pool_kernel");
+}
+
 extern "C" int cffm_cffa_pool_level(const void* xn, int n_frames, int level, int H, int W, int C, const float* pool_w,
                                     const float* pool_b, void* pooled, void* stream) {
   CFFM_REQUIRE(xn && pool_w && pool_b && pooled, CFFM_E_BADARG, "cffa_pool_level: null pointer");
@@ -1117,5 +1176,30 @@ extern "C" int cffm_layernorm_sum(const float* partials, int nsum, const float* 
   else if (nvec <= 96) CFFM_LNS(32, 3);
   else CFFM_LNS(32, 4);
 #undef CFFM_LNS
+  return launch_status("layernorm_kernel");
+}
+
+extern "C" int cffm_layernorm_chain(const float* partials, int nsum, const float* bias, const float* gamma, const float* beta,
+                                    float eps, float* out_f32, int64_t ldo32, const float* gamma2, const float* beta2,
+                                    float eps2, void* out_f16, int64_t ldo16, int M, int C, void* stream) {
+  CFFM_REQUIRE(partials && gamma && beta && gamma2 && beta2 && out_f32 && out_f16, CFFM_E_BADARG, "layernorm_chain: null pointer");
+  CFFM_REQUIRE(M > 0 && C > 0 && nsum >= 1, CFFM_E_BADARG, "layernorm_chain: bad size");
+  CFFM_REQUIRE(C <= 512 && C % 4 == 0, CFFM_E_UNSUPPORTED, "layernorm_chain: need C %% 4 == 0 and C <= 512, got %d", C);
+  CFFM_REQUIRE(ldo16 % 4 == 0 && ldo32 % 4 == 0 && aligned16(gamma) && aligned16(beta) && aligned16(gamma2) && aligned16(beta2) &&
+                   aligned16(partials) && aligned16(bias) && (reinterpret_cast<uintptr_t>(out_f16) & 7) == 0 && aligned16(out_f32),
+               CFFM_E_BADARG, "layernorm_chain: misaligned pointer or stride");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __half* o16 = static_cast<__half*>(out_f16);
+  const int nvec = C / 4;
+  const int64_t stride = static_cast<int64_t>(M) * C;
+#define CFFM_LNC(L, NV) \
+  launch_ln<true, L, NV>(partials, C, gamma, beta, eps, o16, ldo16, out_f32, ldo32, M, C, st, nsum, stride, bias, gamma2, beta2, eps2)
+  if (nvec <= 8) CFFM_LNC(8, 1);
+  else if (nvec <= 16) CFFM_LNC(16, 1);
+  else if (nvec <= 32) CFFM_LNC(32, 1);
+  else if (nvec <= 64) CFFM_LNC(32, 2);
+  else if (nvec <= 96) CFFM_LNC(32, 3);
+  else CFFM_LNC(32, 4);
+#undef CFFM_LNC
   return launch_status("layernorm_kernel");
 }

@@ -177,8 +177,10 @@ class MixVisionTransformer(nn.Module):
         return stages
 
     # ------------------------------------------------------------------ forward
-    def forward_features(self, x):
-        """mix_transformer.py:313-349.  x (N,3,H,W) fp32 -> 4 fp16 NHWC maps returned as NCHW views."""
+    def forward_features(self, x, stage_hook=None):
+        """mix_transformer.py:313-349.  x (N,3,H,W) fp32 -> 4 fp16 NHWC maps returned as NCHW views.
+        ``stage_hook(s, out)`` (optional) is called as soon as stage s is enqueued, so that a consumer can start
+        work that only needs that stage (the decode head's per-stage projection) beside the later stages."""
         if x.dim() != 4 or x.shape[1] != self.in_chans:
             raise _abi.CffmError(f"expected (N,{self.in_chans},H,W) input, got {tuple(x.shape)}")
         plan = self._plan or self._build_plan()
@@ -197,13 +199,15 @@ class MixVisionTransformer(nn.Module):
             xres = ws.get(f"s{s}.x", (M, C), _F)                 # fp32 residual stream
             S = ops.splitk_plan(M, C, st["kpad"])                # few tiles x long K (stages 3-4): split K over the SMs
             pe32 = ws.get(f"s{s}.pe32", (S, M, C), _F)
+            xn = ws.get(f"s{s}.xn", (M, C), _H)
+            b0 = st["blocks"][0]
+            # patch-embed norm and the first block's norm1 in one pass (the row stays in registers in between)
             if S > 1:
                 ops.gemm_splitk(col, st["w"], pe32)
-                ops.layernorm_sum(pe32, st["b"], st["ng"], st["nb"], st["eps"], out32=xres)
+                ops.layernorm_chain(pe32, st["b"], st["ng"], st["nb"], st["eps"], xres, b0["n1g"], b0["n1b"], b0["n1eps"], xn)
             else:
                 ops.gemm(col, st["w"], bias=st["b"], out32=pe32[0])
-                ops.layernorm(pe32[0], st["ng"], st["nb"], st["eps"], out32=xres)
-            xn = ws.get(f"s{s}.xn", (M, C), _H)
+                ops.layernorm_chain(pe32, None, st["ng"], st["nb"], st["eps"], xres, b0["n1g"], b0["n1b"], b0["n1eps"], xn)
             heads = self.num_heads[s]
             d = C // heads
             out = ws.get(f"s{s}.out", (M, C), _H)
@@ -211,7 +215,7 @@ class MixVisionTransformer(nn.Module):
             nblk = len(st["blocks"])
             for bi, b in enumerate(st["blocks"]):
                 # ---- efficient self-attention
-                if bi == 0 or not fuse_ln:
+                if bi > 0 and not fuse_ln:                       # block 0: chained above; fusable widths: in the previous GEMM
                     ops.layernorm(xres, b["n1g"], b["n1b"], b["n1eps"], out16=xn)
                 q = ws.get(f"s{s}.q", (M, C), _H)
                 sr = b["sr"]
@@ -263,11 +267,13 @@ class MixVisionTransformer(nn.Module):
             if not fuse_ln or nblk == 0:
                 ops.layernorm(xres, st["fg"], st["fb"], st["feps"], out16=out)
             outs.append(out.view(N, Ho, Wo, C).permute(0, 3, 1, 2))   # logical NCHW, channels-last memory
+            if stage_hook is not None:
+                stage_hook(s, outs[-1])
             cur, layout, H, W = out, 1, Ho, Wo
         return outs
 
-    def forward(self, x):
-        return self.forward_features(x)
+    def forward(self, x, stage_hook=None):
+        return self.forward_features(x, stage_hook)
 
 
 def _variant(embed_dims, depths):

@@ -99,6 +99,15 @@ def layernorm_sum(partials, bias, gamma, beta, eps, out16=None, out32=None):
               _ld(out16) if out16 is not None else 0, _ptr(out32), _ld(out32) if out32 is not None else 0, M, C, _stream())
 
 
+def layernorm_chain(partials, bias, gamma, beta, eps, out32, gamma2, beta2, eps2, out16):
+    """out32 = LayerNorm(sum_s partials[s] + bias); out16 = LayerNorm2(out32).  partials fp32 [S, M, C]."""
+    _chk(partials, _F, "layernorm_chain.partials"); _chk(out32, _F, "layernorm_chain.out32"); _chk(out16, _H, "layernorm_chain.out16")
+    S, M, C = partials.shape
+    assert partials.is_contiguous() and tuple(out32.shape) == (M, C) == tuple(out16.shape)
+    _abi.call("cffm_layernorm_chain", _ptr(partials), S, _ptr(bias), _ptr(gamma), _ptr(beta), float(eps), _ptr(out32), _ld(out32),
+              _ptr(gamma2), _ptr(beta2), float(eps2), _ptr(out16), _ld(out16), M, C, _stream())
+
+
 def gemm_ln_supported(N):
     return N <= 128 and N % 8 == 0
 
@@ -173,6 +182,15 @@ def cffa_pool(xn, B, T, H, W, C, pool_w, pool_b, pooled):
     _chk(pooled, _H, "cffa_pool.pooled")
     assert pool_w.numel() == 49 + 49 + 9 + 4 and pool_b.numel() == 4 and pooled.is_contiguous()
     _abi.call("cffm_cffa_pool", _ptr(xn), B, T, H, W, C, _ptr(pool_w), _ptr(pool_b), _ptr(pooled), _stream())
+
+
+def cffa_pool_part(xn, B, part, H, W, C, pool_w, pool_b, pooled):
+    """part 0: target level from xn [B,H,W,C]; part 1: reference levels from xn [3,B,H,W,C]; rows of the other part untouched."""
+    _chk(xn, _H, "cffa_pool_part.xn"); _chk(pool_w, _F, "cffa_pool_part.pool_w"); _chk(pool_b, _F, "cffa_pool_part.pool_b")
+    _chk(pooled, _H, "cffa_pool_part.pooled")
+    assert pool_w.numel() == 49 + 49 + 9 + 4 and pool_b.numel() == 4 and pooled.is_contiguous() and xn.is_contiguous()
+    assert xn.numel() == (1 if part == 0 else 3) * B * H * W * C
+    _abi.call("cffm_cffa_pool_part", _ptr(xn), B, part, H, W, C, _ptr(pool_w), _ptr(pool_b), _ptr(pooled), _stream())
 
 
 def cffa_norm_frames(x, gamma, beta, eps, xn, xt_pad, n_frames, first_target, H, W, Hp, Wp, C):
@@ -250,16 +268,21 @@ _side = {}
 
 
 class fork:
-    """``with ops.fork(): ...`` enqueues the body on a side stream that first waits for everything already on the
-    current stream; ``ops.join()`` makes the current stream wait for it.  Independent branches of the forward (q
-    projection vs the spatial-reduction K/V chain, the four decoder projections, QKV vs pooling) then overlap on
-    the GPU; the fork/join pattern is preserved as parallel branches when the pass is captured in a CUDA graph."""
+    """``with ops.fork(key): ...`` enqueues the body on the side stream ``key``, which first waits for everything
+    already on the current stream; ``ops.join(key)`` makes the current stream wait for it.  Independent branches of
+    the forward (q projection vs the spatial-reduction K/V chain, decoder projections vs the later backbone stages,
+    reference-frame assembling vs the target path) then overlap on the GPU; the fork/join pattern is preserved as
+    parallel branches when the pass is captured in a CUDA graph.  Every forked stream must be joined (directly or
+    through another stream) before the pass ends."""
+
+    def __init__(self, key=0):
+        self.key = key
 
     def __enter__(self):
-        dev = torch.cuda.current_device()
-        if dev not in _side:
-            _side[dev] = torch.cuda.Stream(device=dev)
-        self.side = _side[dev]
+        k = (torch.cuda.current_device(), self.key)
+        if k not in _side:
+            _side[k] = torch.cuda.Stream(device=k[0])
+        self.side = _side[k]
         self.side.wait_stream(torch.cuda.current_stream())
         self.ctx = torch.cuda.stream(self.side)
         self.ctx.__enter__()
@@ -270,8 +293,8 @@ class fork:
         return False
 
 
-def join():
-    side = _side.get(torch.cuda.current_device())
+def join(key=0):
+    side = _side.get((torch.cuda.current_device(), key))
     if side is not None:
         torch.cuda.current_stream().wait_stream(side)
 
@@ -280,13 +303,13 @@ class KernelTimer:
     """CUDA-event timing of selected entry points on the launching stream (bench.py's live roofline
     measurement).  ``with KernelTimer({"cffm_cfm_attention"}) as kt: step()`` then ``kt.results()``."""
 
-    def __init__(self, names):
-        self.names = set(names)
+    def __init__(self, names=None):
+        self.names = None if names is None else set(names)      # None: every entry point
         self.records = []                                        # (name, args, start_event, end_event)
         self._open = None
 
     def _hook(self, name, phase, args):
-        if name not in self.names:
+        if self.names is not None and name not in self.names:
             return
         ev = torch.cuda.Event(enable_timing=True)
         ev.record(torch.cuda.current_stream())

@@ -113,7 +113,7 @@ class FrameShardedRunner:
         depth = len(P["blocks"])
         # ---- per-frame work: backbone + folded MLP decoder (cffm_head.py:102-133)
         if n_loc:
-            feats = [head._as_nhwc16(t) for t in model.extract_feat(frames)]
+            feats = [head._as_nhwc16(t) for t in model.backbone(frames)]   # no stage hook: projections are issued below
             sizes = [(t.shape[1], t.shape[2]) for t in feats]
             h, w = sizes[0]
             proj = []

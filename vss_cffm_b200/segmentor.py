@@ -98,6 +98,13 @@ class EncoderDecoder_clips(nn.Module):
 
     # ------------------------------------------------------------------ the hot path
     def extract_feat(self, img):
+        """encoder_decoder.py:323-327.  When both sides are this package's modules the head projects every stage
+        output as soon as the backbone has produced it (beside the later, smaller stages)."""
+        hook = getattr(self.decode_head, "project_stage", None)
+        if hook is not None and hasattr(self.backbone, "forward_features"):
+            outs = self.backbone(img, stage_hook=hook)
+            self.decode_head.early_projections_belong_to(outs)  # valid for exactly this list object
+            return outs
         return self.backbone(img)
 
     def _device(self):
