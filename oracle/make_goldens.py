@@ -162,7 +162,7 @@ def main():
         np.savez_compressed(os.path.join(GOLD, f"mit_{tag}.npz"), **{f"out{i}": o.numpy() for i, o in enumerate(outs)})
 
     # ---------------------------------------------------------------- 6. end-to-end segmentor
-    for tag, T, B, seed in (("b0", 2, 1, 7), ("b0", 4, 1, 7), ("b1", 4, 2, 8)):
+    for tag, T, B, seed in (("b0", 2, 1, 7), ("b0", 4, 1, 7), ("b1", 4, 2, 8), ("b2", 4, 1, 10)):
         m = load_synth(models[tag], seed)
         H, W = 64, 96
         imgs = synth.synth_clip(B, T, H, W, seed=seed)

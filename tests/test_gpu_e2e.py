@@ -107,7 +107,7 @@ def _run_cffm_blocks(head, x):
     return xt.view(B, H, W, C)[0]
 
 
-@pytest.mark.parametrize("tag,T,B,seed,depth", [("b0", 2, 1, 7, 1), ("b0", 4, 1, 7, 1), ("b1", 4, 2, 8, 2)])
+@pytest.mark.parametrize("tag,T,B,seed,depth", [("b0", 2, 1, 7, 1), ("b0", 4, 1, 7, 1), ("b1", 4, 2, 8, 2), ("b2", 4, 1, 10, 2)])
 def test_end_to_end_vs_reference_golden(golden_dir, tag, T, B, seed, depth):
     """EncoderDecoder_clips.forward(return_loss=False) vs the unmodified reference's logits and labels."""
     g = np.load(os.path.join(golden_dir, f"e2e_{tag}_T{T}.npz"))

@@ -87,7 +87,7 @@ def test_mit_backbone(golden_dir, tag, seed):
         _close(o, g[f"out{i}"], rtol=5e-5)
 
 
-@pytest.mark.parametrize("tag,T,B,seed,depth", [("b0", 2, 1, 7, 1), ("b0", 4, 1, 7, 1), ("b1", 4, 2, 8, 2)])
+@pytest.mark.parametrize("tag,T,B,seed,depth", [("b0", 2, 1, 7, 1), ("b0", 4, 1, 7, 1), ("b1", 4, 2, 8, 2), ("b2", 4, 1, 10, 2)])
 def test_end_to_end_segmentor(golden_dir, tag, T, B, seed, depth):
     g = np.load(os.path.join(golden_dir, f"e2e_{tag}_T{T}.npz"))
     sd = synth.synth_state_dict(_spec(golden_dir, tag), seed)

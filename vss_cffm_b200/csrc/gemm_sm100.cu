@@ -54,7 +54,7 @@ struct Epilogue {
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN == 64) ? 5 : 3;
+  static constexpr int STAGES = (BN == 64) ? 5 : 4;
   static constexpr int TEAMS = (BN == 64) ? 2 : 1;  // BN=64: two 8-warp teams alternate tiles (accumulator stage = team)
   static constexpr int TEAM_WARPS = NUM_EPI_WARPS / TEAMS;
   static constexpr int W_STAGE_BYTES = BN * BLOCK_K * 2;
@@ -533,7 +533,10 @@ extern "C" int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t 
   }
   CFFM_REQUIRE(impl == CFFM_GEMM_TCGEN05, CFFM_E_BADARG, "gemm: bad impl %d", impl);
   const bool f16_only = out_f16 != nullptr && out_f32 == nullptr && residual == nullptr;
-  const bool wide = N % 128 == 0 || (N % 64 != 0 && N > 64);
+  // 128-wide tiles halve the A re-reads, but a GEMM with few tiles is latency-bound: 64-wide tiles put twice as many
+  // SMs (and TMA pipelines) on it.  The choice depends on the shape only, never on the data.
+  const int tiles128 = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + 127) / 128);
+  const bool wide = (N % 128 == 0 || (N % 64 != 0 && N > 64)) && !(N % 64 == 0 && tiles128 * 2 <= num_sms());
   if (f16_only) {
     return wide ? launch_tcgen05<128, true>(A, lda, W, ldw, ep, M, N, K, st)
                 : launch_tcgen05<64, true>(A, lda, W, ldw, ep, M, N, K, st);
