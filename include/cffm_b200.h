@@ -219,6 +219,33 @@ int cffm_resize_nchw(const float* in, float* out, int B, int C, int h, int w, in
  * a caller asks for probabilities -- simple_test's argmax skips it. */
 int cffm_softmax_nchw(const float* in, float* out, int B, int C, int64_t HW, void* stream);
 
+/* ---- k-means prototypes of CFFM++ (cffm_head.py:267-294: fast_pytorch_kmeans.KMeans(n_clusters, max_iter=10,
+ * mode='euclidean').fit_predict on the 1/8-scale decoder features of one video).  One Lloyd iteration is
+ *   scores = X c_hi^T + X c_lo^T              two cffm_gemm_f16 calls (fp32 out, second one accumulating)
+ *   cffm_kmeans_assign                         labels, one-hot [Kp, Np_pad] fp16, counts (caller zeroes counts first)
+ *   partials = onehot . Xt^T                   cffm_gemm_f16_splitk
+ *   cffm_kmeans_update                         centroids, error, hi/lo halves and norms for the next iteration
+ * Kp = K rounded up to the GEMM tile (128), Np_pad = Np rounded up to 8. */
+
+/* fp32 centroids [K,E] -> fp16 hi / lo halves [Kp,E] (rows >= K zero) and squared norms [Kp]. */
+int cffm_kmeans_prepare(const float* centroids, void* c_hi, void* c_lo, float* cnorm, int K, int Kp, int E,
+                        void* stream);
+
+/* labels[p] = arg max_j (2 scores[p][j] - cnorm[j]) (first maximum), int64 [Np]; onehot fp16 [Kp, Np_pad];
+ * counts int32 [K] += members (atomic).  scores fp32 [Np, lds]. */
+int cffm_kmeans_assign(const float* scores, int64_t lds, const float* cnorm, int Np, int Np_pad, int K, int Kp,
+                       int64_t* labels, void* onehot, int* counts, void* stream);
+
+/* centroids[j] <- sum_s partials[s][j] / counts[j] (0 for an empty cluster, as the library zeroes the NaN);
+ * *error = sum_j |new - old|^2 (summed in cluster order by the last CTA; `done` is a zero-initialised counter
+ * the kernel resets).  partials fp32 [nsplit, Kp, E]. */
+int cffm_kmeans_update(const float* partials, int nsplit, const int* counts, float* centroids, void* c_hi, void* c_lo,
+                       float* cnorm, float* err_per_cluster, float* error, unsigned int* done, int K, int Kp, int E,
+                       void* stream);
+
+/* x fp16 [rows, cols] -> xt fp16 [cols, rows_pad] (columns >= rows zero). */
+int cffm_transpose_f16(const void* x, int rows, int cols, void* xt, int rows_pad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

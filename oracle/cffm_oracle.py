@@ -325,6 +325,25 @@ def cffm_head_forward(sd, p, feats, batch_size, num_clips, cfg_num_clips, depth,
     return x2
 
 
+def gene_prototype_head_forward(sd, p, feats, batch_size, num_clips, n_clusters=100, max_iter=10, init_centroids=None):
+    """CFFMHead_clips_resize1_8_gene_prototype.forward (cffm_head.py:239-300): linear_pred logits of the last frame,
+    the 1/8-scale clustering features (B, num_clips*h2*w2, C) and the k-means centres (B, K, C).  The k-means itself is
+    the restatement in oracle/kmeans_oracle.py (third-party fast_pytorch_kmeans, parity unpinned)."""
+    from . import kmeans_oracle
+    _c = head_mlp_decoder(sd, p, feats)
+    n, C, h, w = _c.shape
+    x = F.conv2d(_c, sd[p + "linear_pred.weight"], sd[p + "linear_pred.bias"]).reshape(batch_size, num_clips, -1, h, w)
+    assert batch_size == 1                                                   # (:269)
+    h2, w2 = int(h / 2), int(w / 2)
+    c2 = resize(_c, (h2, w2)).reshape(batch_size, num_clips, C, h2, w2)
+    cl = c2.permute(0, 1, 3, 4, 2).reshape(batch_size, num_clips * h2 * w2, C)   # (:273-275)
+    centers = []
+    for ii in range(batch_size):
+        init = None if init_centroids is None else init_centroids[ii]
+        centers.append(kmeans_oracle.fit_predict(cl[ii], n_clusters, max_iter=max_iter, centroids=init)[1])
+    return x[:, -1], cl, torch.stack(centers, dim=0)
+
+
 # =============================================================================== CFFM++
 def cluster_attention(sd, p, x, centers, heads=CFFM_HEADS):
     """WindowAttention_cluster.forward with only_use_cluster_center_as_context=True.

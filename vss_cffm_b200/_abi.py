@@ -44,6 +44,10 @@ SIGNATURES = {
     "cffm_cffa_pool": ([vp, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
     "cffm_cffa_pool_part": ([vp, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
     "cffm_cffa_pool_level": ([vp, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
+    "cffm_kmeans_prepare": ([vp, vp, vp, vp, i32, i32, i32, vp], i32),
+    "cffm_kmeans_assign": ([vp, i64, vp, i32, i32, i32, i32, vp, vp, vp, vp], i32),
+    "cffm_kmeans_update": ([vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp], i32),
+    "cffm_transpose_f16": ([vp, i32, i32, vp, i32, vp], i32),
     "cffm_cfm_attention": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),
     "cffm_cfm_key_sources": ([i32, i32, vp, vp], i32),
     "cffm_resize_nhwc_to_nchw": ([vp, i32, i64, vp, i32, i32, i32, i32, i32, i32, vp], i32),

@@ -525,3 +525,72 @@ class CFFMHead_clips_resize1_8_finetune_w_prototype3(CFFMHead_clips_resize1_8):
 
     def forward_test(self, inputs, img_metas, test_cfg, batch_size=None, num_clips=None, img=None, **kw):
         return self.forward(inputs, batch_size, num_clips, img, img_metas, **kw)
+
+
+@HEADS.register_module()
+class CFFMHead_clips_resize1_8_gene_prototype(CFFMHead_clips_resize1_8):
+    """Prototype generation for CFFM++ (cffm_head.py:161-300): the MLP decoder on every frame, ``linear_pred`` logits of
+    the last frame as the return value, and -- the point of this head -- k-means (K = 100, 10 Lloyd iterations) on the
+    1/8-scale decoder features of the clip, saved as ``<save_path>/<video>/centers.pt`` (a (1, K, 256) fp32 tensor),
+    exactly where ``CFFMHead_clips_resize1_8_finetune_w_prototype3`` reads them.  Same parameters / state-dict keys as
+    the CFFM head (``decoder_focal`` and ``linear_pred2`` exist but are not used by this forward, as in the reference)."""
+
+    EARLY_RETURN_LAST_FRAME = False          # every frame handed in is decoded and clustered (no eval early return, :239-300)
+    FUSED_TAIL = False                       # the segmentor calls forward_test (k-means + file output), not forward_scores
+
+    def __init__(self, feature_strides, **kwargs):
+        super().__init__(feature_strides, **kwargs)
+        self.n_clusters = 100                                     # cffm_head.py:217
+        self.save_path = "./cluster_centers/"
+        self.kmeans_max_iter = 10                                 # cffm_head.py:280
+
+    def forward_test(self, inputs, img_metas, test_cfg, batch_size=None, num_clips=None, img=None, **kw):
+        return self.forward(inputs, batch_size, num_clips, img, img_metas, **kw)
+
+    def cluster_features(self, inputs, batch_size, num_clips, frame_major=False):
+        """(logits of the last frame NHWC fp32 [B*h*w, ncp], 1/8-scale features fp16 [T, B, h2*w2, E], (h, w))."""
+        P = self._plan or self._build_plan()
+        ws = self._ws
+        feats = [self._as_nhwc16(t) for t in self._transform_inputs(inputs)]
+        N = feats[0].shape[0]
+        if N != batch_size * num_clips:
+            raise _abi.CffmError(f"got {N} frames for batch_size={batch_size} x num_clips={num_clips}")
+        E, ncp = self.embed_dim, P["ncp"]
+        sizes = [(t.shape[1], t.shape[2]) for t in feats]
+        h, w = sizes[0]
+        if h % 2 or w % 2:
+            raise _abi.CffmError(f"1/4-scale feature size must be even (got {h}x{w})")
+        B, T = batch_size, num_clips
+        if self._early:
+            ops.join("proj")
+        self._early, self._early_src = {}, None
+        proj = [ws.get(f"p{i}", (N * sizes[i][0] * sizes[i][1], E), _H) for i in range(4)]
+        for i in range(4):
+            ops.gemm(feats[i].reshape(-1, feats[i].shape[3]), P["pw"][i], out16=proj[i])
+        t_perm = 0 if (frame_major or T == 1) else T
+        c_full = ws.get("c_full", (N * h * w, E), _H)
+        HW = (h // 2) * (w // 2)
+        c16 = ws.get("c16", (N * HW, E), _H)
+        ops.head_fuse(proj, sizes, N, E, t_perm, P["shift"], c_full=c_full, half16=c16)
+        lg = ws.get("lg_full", (B * h * w, ncp), _F)
+        ops.gemm(c_full[(T - 1) * B * h * w:], P["pred_w"], bias=P["pred_b"], out32=lg)   # x[:, -1] is all that is returned (:299)
+        return lg, c16.view(T, B, HW, E), (h, w)
+
+    def forward(self, inputs, batch_size=None, num_clips=None, imgs=None, img_metas=None, *, frame_major=False, save=True):
+        from .kmeans import KMeans
+        assert batch_size == 1, "prototype generation runs one video clip at a time (cffm_head.py:269)"
+        lg, feats, (h, w) = self.cluster_features(inputs, batch_size, num_clips, frame_major)
+        centers = []
+        for ii in range(batch_size):                             # clip ii: all its frames' 1/8-scale pixels (:273-283)
+            km = KMeans(n_clusters=self.n_clusters, max_iter=self.kmeans_max_iter, mode="euclidean", verbose=0)
+            km.fit_predict(feats[:, ii].reshape(-1, self.embed_dim))
+            centers.append(km.centroids)
+        self.centers = torch.stack(centers, dim=0)               # (B, K, E) fp32
+        if save and img_metas is not None:
+            video = img_metas[0]["filename"].split("/")[-3]
+            path = self.save_path + video
+            os.makedirs(path, exist_ok=True)
+            torch.save(self.centers.cpu(), path + "/centers.pt")
+        out = torch.empty(batch_size, self.num_classes, h, w, dtype=_F, device=lg.device)
+        ops.resize_nhwc_to_nchw(lg, self.num_classes, out, batch_size, h, w, h, w)
+        return out

@@ -14,7 +14,11 @@ REFERENCE_FILES = {
 REFERENCE_FILES.update({
     (v, "cffmpp"): f"local_configs/cffm/{v.upper()}/cffm.{v}.480x480.vspw2_fine_w_proto.40k.py" for v in IN_CHANNELS
 })
-_HEAD_TYPE = {"cffm": "CFFMHead_clips_resize1_8", "cffmpp": "CFFMHead_clips_resize1_8_finetune_w_prototype3"}
+REFERENCE_FILES.update({
+    (v, "proto"): f"local_configs/cffm/{v.upper()}/cffm.{v}.480x480.vspw2_gene_prototype.py" for v in IN_CHANNELS
+})
+_HEAD_TYPE = {"cffm": "CFFMHead_clips_resize1_8", "cffmpp": "CFFMHead_clips_resize1_8_finetune_w_prototype3",
+              "proto": "CFFMHead_clips_resize1_8_gene_prototype"}
 
 
 def model_cfg(variant="b1", kind="cffm", num_classes=124, num_clips=4, depths=None):

@@ -128,7 +128,7 @@ class EncoderDecoder_clips(nn.Module):
     def _features(self, frames, B, T):
         """Backbone on frame-major frames; on the head's early-return path (eval and T != num_clips,
         cffm_head.py:127-129) only the target frame influences the output, so only it is encoded."""
-        if T != self.decode_head.num_clips:
+        if T != self.decode_head.num_clips and getattr(self.decode_head, "EARLY_RETURN_LAST_FRAME", True):
             return self.extract_feat(frames[-1]), 1
         return self.extract_feat(frames.reshape(T * B, *frames.shape[2:])), T
 
@@ -186,7 +186,7 @@ class EncoderDecoder_clips(nn.Module):
         ori = tuple(img_meta[0]["ori_shape"][:2])
         assert all(tuple(m["ori_shape"][:2]) == ori for m in img_meta)
         head = self.decode_head
-        fused = (not (rescale and ori != (H, W))) and hasattr(head, "forward_scores")
+        fused = (not (rescale and ori != (H, W))) and hasattr(head, "forward_scores") and getattr(head, "FUSED_TAIL", True)
         if fused:
             x, t = self._features(frames, B, T)
             if "img_metas" not in head_kw:
