@@ -319,6 +319,17 @@ def main():
 
     if rank == 0:
         pk = peaks()
+        # DRAM bytes per launch measured by ncu for the same workload (profiles/r01_traffic.json, written by tools/ncu_traffic.py
+        # from a committed capture; null when the file is missing)
+        try:
+            traffic = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")))
+        except Exception:
+            traffic = None
+
+        def ncu_traffic(family):
+            f = (traffic or {}).get("families", {}).get(family)
+            return None if f is None else {"dram_bytes_per_launch": f["dram_bytes_per_launch"], "launches_per_step": f["launches_per_step"],
+                                           "capture": traffic["source"]}
         # ---- dominant kernel family: the tcgen05 GEMM (every Linear / conv of the path).  Algorithmic bytes of a
         # launch = A + W + bias + residual + outputs, each once; FLOPs = 2 M N K.
         gem = {}
@@ -337,7 +348,7 @@ def main():
         top = sorted(gem.items(), key=lambda kv: -kv[1][1])[:5]
         gbs = g_bytes / (g_ms * 1e-3) / 1e9 if g_ms else 0.0
         roofline = {"kernel": "gemm_tcgen05_kernel (all launches of the step)", "bound": "hbm", "achieved": round(gbs, 1),
-                    "peak": pk["hbm"], "unit": "GB/s", "frac": round(gbs / pk["hbm"], 4), "traffic": None,
+                    "peak": pk["hbm"], "unit": "GB/s", "frac": round(gbs / pk["hbm"], 4), "traffic": ncu_traffic("gemm_tcgen05_kernel"),
                     "tensor_tflops": round(g_flops / (g_ms * 1e-3) / 1e12, 2) if g_ms else 0.0,
                     "launches_per_step": n_gemm // ksteps, "ms_per_step": round(g_ms / ksteps, 4),
                     "share_of_kernel_time": round(g_ms / eager_ms, 4), "peak_source": pk["src"],
@@ -354,7 +365,7 @@ def main():
         cgbs = alg_bytes / (cfm_avg_ms * 1e-3) / 1e9
         ctfs = alg_flops / (cfm_avg_ms * 1e-3) / 1e12
         roofline_cfm = {"kernel": "cfm_attention_kernel", "bound": "hbm", "achieved": round(cgbs, 2), "peak": pk["hbm"],
-                        "unit": "GB/s", "frac": round(cgbs / pk["hbm"], 5), "traffic": None,
+                        "unit": "GB/s", "frac": round(cgbs / pk["hbm"], 5), "traffic": ncu_traffic("cfm_attention_kernel"),
                         "tensor_tflops": round(ctfs, 3), "tensor_frac_of_sustained": round(ctfs / pk["tf_sust"], 5),
                         "launch_ms": round(cfm_avg_ms, 5), "launches_timed": len(cfm_ms),
                         "share_of_kernel_time": round(sum(cfm_ms) / eager_ms, 4),

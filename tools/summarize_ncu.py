@@ -56,7 +56,7 @@ def main():
                         g(d, "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
                         g(d, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
                         g(d, "sm__warps_active.avg.pct_of_peak_sustained_active"), g(d, "launch__registers_per_thread"))
-                f.write(f"{i},{d['name']},\"{d['grid']}\",\"{d['block']}\"," + ",".join(f"{v:.2f}" for v in vals) + "\n")
+                f.write(f"{i},\"{d['name']}\",\"{d['grid']}\",\"{d['block']}\"," + ",".join(f"{v:.2f}" for v in vals) + "\n")
                 if not d["name"].startswith("at::"):
                     out.append(f"| {i} | `{d['name'][:40]}` | {d['grid']} | {vals[0]:.1f} | {vals[1] / 1e6:.1f} | {vals[2] / 1e6:.1f} | "
                                f"{vals[3]:.1f} | {vals[4]:.1f} | {vals[5]:.1f} | {vals[6]:.1f} | {vals[7]:.0f} |")
