@@ -139,7 +139,7 @@ def test_layernorm_chain(ops, S, M, C):
     check(o32, F.layer_norm(parts[0].double(), (C,), g1.double(), b1.double(), 1e-5), REL32, "chain: no bias")
 
 
-@pytest.mark.parametrize("layout,N,H,W,C,k,s,p", [(0, 2, 64, 96, 3, 7, 4, 3), (1, 2, 16, 24, 64, 3, 2, 1),
+@pytest.mark.parametrize("layout,N,H,W,C,k,s,p", [(0, 2, 64, 96, 3, 7, 4, 3), (0, 1, 30, 50, 3, 7, 4, 3), (0, 2, 480, 480, 3, 7, 4, 3), (1, 2, 16, 24, 64, 3, 2, 1),
                                                   (1, 1, 16, 24, 32, 8, 8, 0), (1, 3, 9, 7, 160, 3, 2, 1),
                                                   (1, 2, 8, 12, 128, 4, 4, 0)])
 def test_im2col_bit_exact(ops, layout, N, H, W, C, k, s, p):

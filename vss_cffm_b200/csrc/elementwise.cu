@@ -178,14 +178,17 @@ im2col_nhwc_kernel(const __half* __restrict__ x, int N, int H, int W, int C, int
 }
 
 // fp32 NCHW image -> fp16 patches.  One CTA per output row (n, oy): the k input rows of every channel are
-// staged in shared memory with coalesced reads (fp32 -> fp16 once), then each thread assembles 16-byte
+// staged in shared memory (fp32 -> fp16 once; 16-byte loads, all of a thread's loads issued before the first
+// conversion so that ~10 requests per thread are in flight), then each thread assembles 16-byte
 // chunks of the patch matrix, so the (dominant) output traffic is written as full 16-byte stores.
+// Shared rows are [C*k][Wp] with the image starting at column PADL (= pad rounded up to 4: 8-byte aligned stores).
 __global__ void __launch_bounds__(256)
 im2col_nchw_f32_kernel(const float* __restrict__ x, int N, int H, int W, int C, int k, int stride, int pad, int Ho,
                        int Wo, __half* __restrict__ A, int Kpad) {
   pdl_sync();
   extern __shared__ __align__(16) uint8_t im_smem[];
-  const int Wp = W + 2 * pad;
+  const int PADL = (pad + 3) & ~3;
+  const int Wp = ((W + PADL + pad + 3) & ~3);
   const int kdim = k * k * C, chunks = Kpad / 8;
   __half* rows = reinterpret_cast<__half*>(im_smem);           // [C*k][Wp] (zero borders)
   int* lut = reinterpret_cast<int*>(im_smem + ((static_cast<size_t>(C) * k * Wp * 2 + 15) & ~static_cast<size_t>(15)));   // [Kpad]
@@ -195,18 +198,54 @@ im2col_nchw_f32_kernel(const float* __restrict__ x, int N, int H, int W, int C, 
     int off = -1;
     if (kc < kdim) {
       const int c = kc % C, tap = kc / C, kx = tap % k, ky = tap / k;
-      off = (c * k + ky) * Wp + kx;
+      off = (c * k + ky) * Wp + kx + (PADL - pad);
     }
     lut[kc] = off;
   }
-  for (int r = warp; r < C * k; r += 8) {                      // one (channel, ky) input row per warp pass
-    const int ky = r % k, c = r / k;
-    const int iy = oy * stride - pad + ky;
-    const bool rv = iy >= 0 && iy < H;
-    const float* src = x + ((static_cast<int64_t>(n) * C + c) * H + (rv ? iy : 0)) * W;
-    for (int xp = lane; xp < Wp; xp += 32) {
-      const int xx = xp - pad;
-      rows[r * Wp + xp] = __float2half_rn(rv && xx >= 0 && xx < W ? src[xx] : 0.f);
+  const int nrows = C * k;
+  if ((W & 3) == 0) {
+    const int W4 = W >> 2, items = nrows * W4;
+    for (int r = threadIdx.x; r < nrows; r += 256) {            // zero borders
+      for (int q = 0; q < PADL; ++q) rows[r * Wp + q] = __float2half_rn(0.f);
+      for (int q = PADL + W; q < Wp; ++q) rows[r * Wp + q] = __float2half_rn(0.f);
+    }
+    constexpr int U = 10;                                       // loads in flight per thread
+    for (int i0 = threadIdx.x; i0 < items; i0 += 256 * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 256;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < items) {
+          const int r = i / W4, x4 = i - r * W4;
+          const int ky = r % k, c = r / k;
+          const int iy = oy * stride - pad + ky;
+          if (iy >= 0 && iy < H)
+            v[u] = *reinterpret_cast<const float4*>(x + ((static_cast<int64_t>(n) * C + c) * H + iy) * W + 4 * x4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 256;
+        if (i < items) {
+          const int r = i / W4, x4 = i - r * W4;
+          uint2 h;
+          h.x = pack_half2(v[u].x, v[u].y);
+          h.y = pack_half2(v[u].z, v[u].w);
+          *reinterpret_cast<uint2*>(rows + r * Wp + PADL + 4 * x4) = h;
+        }
+      }
+    }
+  } else {
+    for (int r = warp; r < nrows; r += 8) {                    // one (channel, ky) input row per warp pass
+      const int ky = r % k, c = r / k;
+      const int iy = oy * stride - pad + ky;
+      const bool rv = iy >= 0 && iy < H;
+      const float* src = x + ((static_cast<int64_t>(n) * C + c) * H + (rv ? iy : 0)) * W;
+      for (int xp = lane; xp < Wp; xp += 32) {
+        const int xx = xp - PADL;
+        rows[r * Wp + xp] = __float2half_rn(rv && xx >= 0 && xx < W ? src[xx] : 0.f);
+      }
     }
   }
   __syncthreads();
@@ -257,9 +296,10 @@ __device__ __forceinline__ void store_halves(__half* __restrict__ p, const float
   *reinterpret_cast<typename HalfVec<CPT>::T*>(p) = raw;
 }
 
-// One column strip.  INTERIOR: all PXW + 2 input columns and all PXW output columns are inside the image, so no
-// per-column predicates; CT > 0: the channel count is a compile-time constant and every load / store of a row is
-// `row pointer + immediate` (the integer address arithmetic was ~35 % of the issued instructions before).
+// One column strip.  INTERIOR: all (PXW + 2) x (RS + 2) inputs and all PXW x RS outputs are inside the image, so the
+// strip is straight-line code -- no row / column predicates and no branches, which lets the compiler issue the loads of
+// the next input row under the FMAs of the current one; CT > 0: the channel count is a compile-time constant and every
+// load / store of a row is `row pointer + immediate` (integer address arithmetic was ~35 % of the issued instructions).
 template <int CPT, int PXW, int RS, int CT, bool INTERIOR>
 __device__ __forceinline__ void dwconv_strip(const __half* __restrict__ xin_n, __half* __restrict__ out_n,
                                              const float (&wf)[9][CPT], const float (&bs)[CPT], int x0, int y0, int H,
@@ -272,7 +312,7 @@ __device__ __forceinline__ void dwconv_strip(const __half* __restrict__ xin_n, _
 #pragma unroll
   for (int r = 0; r < RS + 2; ++r, rp += row_stride) {
     const int iy = y0 - 1 + r;
-    if (iy >= 0 && iy < H) {
+    if (INTERIOR || (iy >= 0 && iy < H)) {
       float xin[PXW + 2][CPT];
 #pragma unroll
       for (int j = 0; j < PXW + 2; ++j) {
@@ -305,7 +345,7 @@ __device__ __forceinline__ void dwconv_strip(const __half* __restrict__ xin_n, _
         for (int e = 0; e < CPT; ++e) acc[r % 3][px][e] = bs[e];
     }
     if (r >= 2) {                                               // output row q = r - 2 is complete
-      if (y0 + r - 2 < H) {
+      if (INTERIOR || y0 + r - 2 < H) {
 #pragma unroll
         for (int px = 0; px < PXW; ++px) {
           if (INTERIOR || x0 + px < W) {
@@ -344,7 +384,8 @@ dwconv3x3_gelu_rows_kernel(const __half* __restrict__ x, const __half* __restric
   }
   const __half* xin_n = x + static_cast<int64_t>(n) * H * W * C + c;
   __half* out_n = out + static_cast<int64_t>(n) * H * W * C + c;
-  if (x0 >= 1 && x0 + PXW + 1 <= W) dwconv_strip<CPT, PXW, RS, CT, true>(xin_n, out_n, wf, bs, x0, y0, H, W, C);
+  if (x0 >= 1 && x0 + PXW + 1 <= W && y0 >= 1 && y0 + RS + 1 <= H)
+    dwconv_strip<CPT, PXW, RS, CT, true>(xin_n, out_n, wf, bs, x0, y0, H, W, C);
   else dwconv_strip<CPT, PXW, RS, CT, false>(xin_n, out_n, wf, bs, x0, y0, H, W, C);
 }
 
@@ -955,9 +996,11 @@ extern "C" int cffm_im2col(const void* x, int layout, int N, int H, int W, int C
         static_cast<const __half*>(x), N, H, W, C, k, stride, pad, Ho, Wo, static_cast<__half*>(A), Kpad);
   } else {
     CFFM_REQUIRE(layout == 0, CFFM_E_BADARG, "im2col: bad layout %d", layout);
-    const int smem = ((C * k * (W + 2 * pad) * 2 + 15) & ~15) + Kpad * 4;
+    const int padl = (pad + 3) & ~3, wp = (W + padl + pad + 3) & ~3;
+    const int smem = ((C * k * wp * 2 + 15) & ~15) + Kpad * 4;
     CFFM_REQUIRE(smem <= 200 * 1024 && aligned16(A), CFFM_E_UNSUPPORTED,
                  "im2col: NCHW path stages C*k*(W+2*pad) halves (%d bytes) in shared memory", smem);
+    CFFM_REQUIRE(aligned16(x), CFFM_E_BADARG, "im2col: misaligned input");
     static cudaError_t e = cudaFuncSetAttribute(im2col_nchw_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     CFFM_REQUIRE(e == cudaSuccess, -(int)e, "im2col: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     launch_k(im2col_nchw_f32_kernel, N * Ho, 256, smem, st, static_cast<const float*>(x), N, H, W, C, k, stride, pad, Ho, Wo,

@@ -24,8 +24,6 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // 64 halves = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 16;                 // four per TMEM lane quarter; one 32x32 chunk per warp per tile
-constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int STG_LD = 36;                        // padded fp32 row of the per-warp 32x32 transpose buffer
 constexpr int STG_BYTES = 5120;                   // per epilogue warp, 512-byte aligned: 32x36 fp32 transpose buffer, or a 32 x 64 B
@@ -52,16 +50,25 @@ struct Epilogue {
   int64_t split_stride;
 };
 
-template <int BN>
+// EW = number of epilogue warps.  16: one CTA per SM, the throughput configuration (big GEMMs).  8 (BN = 64 only): a CTA
+// of 10 warps and <= 112 KB of shared memory, so TWO CTAs share an SM -- the latency configuration for the GEMMs with few
+// tiles (stages 3-4, the head): one CTA's TMA round trips hide behind the other's epilogue, and under programmatic
+// dependent launch the next GEMM's prologue can start while this one still occupies half of the SM.
+template <int BN, int EW, bool F16_ONLY>
 struct Cfg {
-  static constexpr int STAGES = (BN == 64) ? 5 : 4;
-  static constexpr int TEAMS = (BN == 64) ? 2 : 1;  // BN=64: two 8-warp teams alternate tiles (accumulator stage = team)
-  static constexpr int TEAM_WARPS = NUM_EPI_WARPS / TEAMS;
+  static_assert(EW == 16 || (EW == 8 && BN == 64), "8 epilogue warps are built for 64-wide tiles");
+  static constexpr int STAGES = EW == 8 ? 3 : ((BN == 64) ? 5 : 4);
+  static constexpr int TEAMS = EW / 4 / (BN / 32);  // BN=64, 16 warps: two 8-warp teams alternate tiles (accumulator stage = team)
+  static constexpr int TEAM_WARPS = EW / TEAMS;
+  static constexpr int THREADS = 64 + EW * 32;
+  static constexpr int MIN_CTAS = EW == 8 ? 2 : 1;
   static constexpr int W_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + W_STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;        // double-buffered accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    8192 /*LayerNorm row-statistics exchange*/;
+  // per-warp staging: 32x36 fp32 transpose buffer + bias slice, or (fp16-only) a 512-byte aligned 32 x 64 B swizzled tile
+  static constexpr int STG = EW == 8 ? (F16_ONLY ? 2560 : 32 * STG_LD * 4 + 128) : STG_BYTES;
+  static constexpr int LN_BYTES = EW == 8 ? 0 : 8192;   // LayerNorm row-statistics exchange (16-warp kernels only)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EW * STG + 1024 /*align slack*/ + 256 /*barriers*/ + LN_BYTES;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -76,12 +83,13 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, accumulator stage = tile parity
 //   warps 2..17 epilogue: tcgen05.ld (thread = row) -> per-warp smem transpose -> row-contiguous
 //               global accesses for residual / fp32 / fp16 (+ optional fused LayerNorm); overlaps the mainloop
-template <int BN, bool F16_ONLY, bool LN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, bool F16_ONLY, bool LN, int EW>
+__global__ void __launch_bounds__(Cfg<BN, EW, F16_ONLY>::THREADS, Cfg<BN, EW, F16_ONLY>::MIN_CTAS)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO, const Epilogue ep, const int M, const int N, const int K, const int n_tiles_n,
                     const int n_tiles) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EW, F16_ONLY>;
+  static_assert(!LN || EW == 16, "the fused LayerNorm lives in the 16-warp kernel");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -89,12 +97,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* sA = smem;
   uint8_t* sW = smem + C::STAGES * A_STAGE_BYTES;
   float* stg_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + NUM_EPI_WARPS * STG_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + EW * C::STG);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tfull_bar = empty_bar + C::STAGES;                 // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;                        // [2] accumulator drained
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* lnbuf = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + NUM_EPI_WARPS * STG_BYTES + 256);   // [2][4][2][32]
+  float* lnbuf = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + EW * C::STG + 256);   // [2][4][2][32]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -185,9 +193,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int wq = warp & 3;                                   // TMEM lane quarter this warp may access
     const int cg = (ew >> 2) % (BN / 32);
     const int tm = (ew >> 2) / (BN / 32);                      // 0 for BN = 128
-    uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg_all) + ew * STG_BYTES;
+    uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg_all) + ew * C::STG;
     float* stg = reinterpret_cast<float*>(stg8);
-    float* sbias = reinterpret_cast<float*>(stg8 + STG_BYTES - 128);   // [32] bias slice of this warp
+    float* sbias = reinterpret_cast<float*>(stg8 + C::STG - 128);      // [32] bias slice of this warp
     const int rsub = lane >> 3, csub = (lane & 7) * 4;         // after the fp32 transpose: 4 rows x 8 float4 per pass
     const int tstep = static_cast<int>(gridDim.x) * C::TEAMS;
     uint32_t it = tm;
@@ -475,9 +483,10 @@ static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_
 
 namespace {
 
-template <int BN, bool F16_ONLY, bool LN = false>
+template <int BN, bool F16_ONLY, bool LN = false, int EW = 16>
 int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const Epilogue& ep, int M, int N, int K,
                    cudaStream_t st) {
+  using C = Cfg<BN, EW, F16_ONLY>;
   CUtensorMap tmA, tmW;
   int rc = make_tmap(&tmA, A, M, K, lda, BLOCK_M);
   if (rc) return rc;
@@ -491,15 +500,27 @@ int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, F16_ONLY, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg<BN>::SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, F16_ONLY, LN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::SMEM_BYTES);
   });
   CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
   const int tiles = tiles_n * tiles_m * ep.splits;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  launch_k(gemm_tcgen05_kernel<BN, F16_ONLY, LN>, grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st, tmA, tmW, tmO, ep, M, N, K, tiles_n, tiles);
+  const int slots = num_sms() * C::MIN_CTAS;
+  const int grid = tiles < slots ? tiles : slots;
+  launch_k(gemm_tcgen05_kernel<BN, F16_ONLY, LN, EW>, grid, C::THREADS, C::SMEM_BYTES, st, tmA, tmW, tmO, ep, M, N, K, tiles_n, tiles);
   return launch_status("gemm_tcgen05_kernel");
+}
+
+// Few-tile GEMMs (latency-bound) run as 64-wide tiles in the two-CTAs-per-SM configuration.  The limit is in units of
+// 128 x 64 tiles; it depends on the shape only (never on the data), and the per-element summation order over K is the
+// same in every configuration, so the choice cannot change a result bit.
+int small_gemm_max_tiles() {
+  static const int v = [] {
+    const char* e = getenv("CFFM_GEMM_SMALL_TILES");           // tuning override
+    return e ? atoi(e) : 300;                                 // measured: beyond ~2 waves of the 296 CTA slots the 16-warp kernel wins
+  }();
+  return v;
 }
 
 }  // namespace
@@ -533,10 +554,12 @@ extern "C" int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t 
   }
   CFFM_REQUIRE(impl == CFFM_GEMM_TCGEN05, CFFM_E_BADARG, "gemm: bad impl %d", impl);
   const bool f16_only = out_f16 != nullptr && out_f32 == nullptr && residual == nullptr;
-  // 128-wide tiles halve the A re-reads, but a GEMM with few tiles is latency-bound: 64-wide tiles put twice as many
-  // SMs (and TMA pipelines) on it.  The choice depends on the shape only, never on the data.
-  const int tiles128 = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + 127) / 128);
-  const bool wide = (N % 128 == 0 || (N % 64 != 0 && N > 64)) && !(N % 64 == 0 && tiles128 * 2 <= num_sms());
+  const int tiles64 = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + 63) / 64);
+  if (tiles64 <= small_gemm_max_tiles()) {
+    return f16_only ? launch_tcgen05<64, true, false, 8>(A, lda, W, ldw, ep, M, N, K, st)
+                    : launch_tcgen05<64, false, false, 8>(A, lda, W, ldw, ep, M, N, K, st);
+  }
+  const bool wide = N % 128 == 0 || (N % 64 != 0 && N > 64);   // 128-wide tiles halve the A re-reads of the big GEMMs
   if (f16_only) {
     return wide ? launch_tcgen05<128, true>(A, lda, W, ldw, ep, M, N, K, st)
                 : launch_tcgen05<64, true>(A, lda, W, ldw, ep, M, N, K, st);
@@ -583,6 +606,8 @@ extern "C" int cffm_gemm_f16_splitk(const void* A, int64_t lda, const void* W, i
   Epilogue ep{nullptr, nullptr, 0, nullptr, 0, partials, N, CFFM_ACT_NONE, nullptr, nullptr, 0.f, nullptr, 0,
               splits, kb_per, static_cast<int64_t>(M) * N};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int tiles64 = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + 63) / 64) * splits;
+  if (tiles64 <= small_gemm_max_tiles()) return launch_tcgen05<64, false, false, 8>(A, lda, W, ldw, ep, M, N, K, st);
   const bool wide = N % 128 == 0 || (N % 64 != 0 && N > 64);
   return wide ? launch_tcgen05<128, false>(A, lda, W, ldw, ep, M, N, K, st) : launch_tcgen05<64, false>(A, lda, W, ldw, ep, M, N, K, st);
 }
