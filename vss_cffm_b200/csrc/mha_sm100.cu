@@ -4,7 +4,7 @@
 // Persistent CTAs loop over work items (frame b, head h, 128-query tile).  Per item:
 //   TMA      Q tile [128 x 64], K [256 x 64], V [256 x 64] (fp16, 128-byte swizzle) -> shared memory
 //   tcgen05  S[128 x 256] = Q K^T   (A = Q, B = K, both K-major; fp32 accumulator in TMEM columns 0..255)
-//   softmax  8 warps: thread = (row, 128-column half); two passes over S straight out of TMEM (max, then
+//   softmax  16 warps: thread = (row, 64-column quarter); two passes over S straight out of TMEM (max, then
 //            exp2 / sum / fp16 pack); P is written to shared memory in the K-major swizzled A-operand layout,
 //            one 64-key chunk at a time, and handed to the MMA warp chunk by chunk
 //   tcgen05  O[128 x 64] += P_chunk V_chunk  (A = P K-major, B = V MN-major: V is used as loaded, no transpose;
@@ -12,7 +12,8 @@
 // S is double-buffered in TMEM (2 x 256 columns): Q K^T of item i+1 is issued before P V of item i.
 //   epilogue O / rowsum -> fp16 -> global
 // Keys >= N_kv (rows of the next frame, or TMA zero fill past the end) are masked to -inf before the softmax.
-// Warp roles: 0..7 softmax / epilogue, 8 TMA producer, 9 TMEM allocator + MMA issuer.
+// Warp roles: 0..15 softmax / epilogue (4 per scheduler: the exp2 chains of one warp hide behind the others), 16 TMA
+// producer, 17 TMEM allocator + MMA issuer.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -23,9 +24,10 @@ namespace {
 
 constexpr int QT = 128, KV_MAX = 256, D = 64;
 constexpr int Q_BYTES = QT * D * 2, KV_BYTES = KV_MAX * D * 2, P_CHUNK_BYTES = QT * 64 * 2;
-constexpr int SMEM_MHA = Q_BYTES + 3 * KV_BYTES + 4 * P_CHUNK_BYTES + 2 * 2 * QT * 4 /*row max / sum exchange*/ +
+constexpr int SMEM_MHA = Q_BYTES + 3 * KV_BYTES + 4 * P_CHUNK_BYTES + 2 * 4 * QT * 4 /*row max / sum exchange*/ +
                          256 /*barriers*/ + 1024 /*align slack*/;
-constexpr int MHA_THREADS = 320;
+constexpr int SM_WARPS = 16;                      // softmax / epilogue warps: 4 TMEM lane quarters x 4 column quarters
+constexpr int MHA_THREADS = (SM_WARPS + 2) * 32;
 constexpr float LOG2E = 1.4426950408889634f;
 
 // K-major / MN-major 128-byte-swizzled operand descriptor: 8-row (or 8-key) groups of 1024 bytes
@@ -43,7 +45,7 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sV = sK + KV_BYTES;                                 // 2 buffers
   uint8_t* sP = sV + 2 * KV_BYTES;                             // 4 chunks of [128 rows][64 keys]
   float* xmax = reinterpret_cast<float*>(sP + 4 * P_CHUNK_BYTES);   // [2 halves][128 rows]
-  float* xsum = xmax + 2 * QT;
+  float* xsum = xmax + 4 * QT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(xsum + 2 * QT);
   uint64_t* qk_full = bars + 0;    // TMA -> MMA: Q and K landed
   uint64_t* qk_empty = bars + 1;   // MMA -> TMA: Q, K consumed
@@ -59,19 +61,19 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int qtiles = (Nq + QT - 1) / QT;
   const int n_items = batch * heads * qtiles;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == SM_WARPS && lane == 0) {
     ptx::prefetch_tensormap(&tmQ);
     ptx::prefetch_tensormap(&tmK);
     ptx::prefetch_tensormap(&tmV);
     ptx::mbar_init(qk_full, 1); ptx::mbar_init(qk_empty, 1);
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&v_full[b], 1); ptx::mbar_init(&v_empty[b], 1); ptx::mbar_init(&s_full[b], 1);
-      ptx::mbar_init(&o_full[b], 1); ptx::mbar_init(&o_empty[b], 8);
+      ptx::mbar_init(&o_full[b], 1); ptx::mbar_init(&o_empty[b], SM_WARPS);
     }
     for (int c = 0; c < 4; ++c) ptx::mbar_init(&p_full[c], 4);
     ptx::fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == SM_WARPS + 1) {
     ptx::tmem_alloc(tmem_base_smem, 512);
     ptx::tmem_relinquish();
   }
@@ -85,7 +87,7 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   // columns are dead once P chunk 0 has been produced, which is exactly when the first PV MMA is issued.  The MMA
   // warp issues Q K^T of item i+1 (other buffer) before P V of item i, so the tensor pipe works on the next tile
   // while the softmax warps are busy with the current one.
-  if (warp == 8) {
+  if (warp == SM_WARPS) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       uint32_t it = 0;
@@ -101,7 +103,7 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ptx::tma_load_2d(sV + buf * KV_BYTES, &tmV, &v_full[buf], h * D, b * Nkv);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == SM_WARPS + 1) {
     if (lane == 0) {
       // ===================== MMA issuer (one thread) =====================
       constexpr uint32_t idesc_qk = ptx::make_idesc_f16(QT, KV_MAX);                    // A, B K-major
@@ -142,17 +144,17 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // ===================== softmax + epilogue: thread = (row, column half) =====================
-    const int wq = warp & 3, hf = warp >> 2;                   // TMEM lane quarter, column half
+    const int wq = warp & 3, cf = warp >> 2;                   // TMEM lane quarter, 64-column quarter (= P chunk)
     const int row = wq * 32 + lane;                            // row of the query tile = TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    const int bar_id = 1 + wq;                                 // pairs warp w with warp w + 4 (same rows)
+    const int bar_id = 1 + wq;                                 // the four warps that share the same 32 rows
 
     // pass 1: scaled row maximum of the item whose scores sit in TMEM buffer `buf`
     auto row_max = [&](uint32_t buf) -> float {
       float m = -INFINITY;
 #pragma unroll 1
-      for (int sc = 0; sc < 4; ++sc) {
-        const int c0 = hf * 128 + sc * 32;
+      for (int sc = 0; sc < 2; ++sc) {
+        const int c0 = cf * 64 + sc * 32;
         if (c0 >= Nkv) break;                                  // warp-uniform
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(lane_addr + buf * KV_MAX + c0, v);
@@ -171,11 +173,11 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (c0 + j < Nkv) m = fmaxf(m, __uint_as_float(v[j]));
         }
       }
-      xmax[hf * QT + row] = m;
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      const float mo = xmax[(hf ^ 1) * QT + row];
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // xmax may be overwritten by the next call
-      return fmaxf(m, mo) * scale_log2e;                       // positive scale; N_kv >= 1: finite
+      xmax[cf * QT + row] = m;
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      const float mo = fmaxf(fmaxf(xmax[row], xmax[QT + row]), fmaxf(xmax[2 * QT + row], xmax[3 * QT + row]));
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");     // xmax may be overwritten by the next call
+      return mo * scale_log2e;                                 // positive scale; N_kv >= 1: finite
     };
 
     uint32_t it = 0;
@@ -191,9 +193,8 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t s_addr = lane_addr + buf * KV_MAX;
       // ---- pass 2: p = exp2(s * scale - m), row sum, fp16 P chunks in the swizzled A-operand layout
       float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll 1
-      for (int j2 = 0; j2 < 2; ++j2) {
-        const int c = hf * 2 + j2;                             // 64-key chunk
+      {
+        const int c = cf;                                      // this warp's 64-key chunk
         uint8_t* prow = sP + c * P_CHUNK_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll 1
         for (int sc = 0; sc < 2; ++sc) {
@@ -234,9 +235,9 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&p_full[c]);
       }
-      xsum[hf * QT + row] = sum0 + sum1;
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      const float inv = 1.f / (sum0 + sum1 + xsum[(hf ^ 1) * QT + row]);
+      xsum[cf * QT + row] = sum0 + sum1;
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      const float inv = 1.f / ((xsum[row] + xsum[QT + row]) + (xsum[2 * QT + row] + xsum[3 * QT + row]));   // same order in all 4 threads
       // ---- pass 1 of the NEXT item (its Q K^T was issued before this item's P V): hides the P V tail
       float m_next = 0.f;
       if (item + static_cast<int>(gridDim.x) < n_items) {
@@ -244,20 +245,20 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ptx::tc_fence_after();
         m_next = row_max(buf ^ 1u);
       }
-      // ---- epilogue: O[row, 32 hf .. +32) / rowsum -> fp16 -> global
+      // ---- epilogue: O[row, 16 cf .. +16) / rowsum -> fp16 -> global
       ptx::mbar_wait(&o_full[buf], bph);
       ptx::tc_fence_after();
-      uint32_t o[32];
-      ptx::tmem_ld_32x32b_x32(s_addr + hf * 32, o);
+      uint32_t o[16];
+      ptx::tmem_ld_32x32b_x16(s_addr + cf * 16, o);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&o_empty[buf]);
       const int qrow = qt * QT + row;
       if (qrow < Nq) {
-        __half* dst = out + (static_cast<int64_t>(b) * Nq + qrow) * ldo + h * D + hf * 32;
+        __half* dst = out + (static_cast<int64_t>(b) * Nq + qrow) * ldo + h * D + cf * 16;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           uint4 w;
           w.x = pack_half2(__uint_as_float(o[g * 8]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
           w.y = pack_half2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
@@ -271,7 +272,7 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc(tmem_base, 512);
+  if (warp == SM_WARPS + 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
