@@ -226,6 +226,24 @@ def test_full_size_clip_independence_and_determinism(full_model):
         assert torch.equal(alone[0], both[b]), f"clip {b} differs when run alone"
 
 
+@pytest.mark.parametrize("tag,H,W,depth", [("b0", 480, 864, 1), ("b1", 480, 480, 2)])
+def test_full_size_vs_oracle(tag, H, W, depth):
+    """The sizes the reference really runs (VSPW 480p: 480x853 -> AlignedResize(32) = 480x864, non-square, 405 reduced keys
+    per frame; and the 480x480 bench size) against the fp32 CPU oracle, one clip, whole path."""
+    m = build(tag, seed=31)
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    imgs = synth.synth_clip(1, 4, H, W, seed=31)
+    metas = [synth.img_metas(1, H, W)]
+    pred = np.stack(m(img=[imgs], img_metas=metas, return_loss=False))
+    frames, _, _ = m._stack(imgs)
+    logits = m.encode_decode_frames(frames, metas[0], 1, 4).float().cpu()
+    ref_pred, ref_logits = O.segmentor_simple_test(sd, imgs, "mit_" + tag, depth, return_logits=True)
+    e = rel_err(logits, ref_logits)
+    agree = float((pred == ref_pred.numpy()).mean())
+    print(f"full size {tag} {H}x{W}: logits rel err {e:.2e}, label agreement {agree:.4f}")
+    assert pred.shape == (1, H, W) and e <= 1e-2 and agree >= 0.99, (e, agree)
+
+
 def test_full_size_reference_frames_do_not_leak_between_clips(full_model):
     """Changing the reference frames of clip 1 must not change clip 0's labels, and must change clip 1's."""
     m = full_model

@@ -42,6 +42,13 @@ elif which == "mha":
     Nf, Nq, Nkv, heads, d = 8, 14400, 225, 1, 64
     q, kv, out = rn(Nf * Nq, 64).half(), rn(Nf * Nkv, 128).half(), torch.empty(Nf * Nq, 64, device="cuda", dtype=torch.half)
     fn = lambda: ops.mha(q, kv[:, :64], kv[:, 64:], out, Nf, Nq, Nkv, heads, d, d ** -0.5)
+elif which == "cfm":
+    B, H, W, E = 2, 60, 60, 256
+    Hp = Wp = 63
+    nW = 81
+    qkv_t, kvp = rn(B * Hp * Wp, 3 * E).half(), rn(B * 15 * nW, 2 * E).half()
+    bias, out = rn(8, 64, 320) * 0.1, torch.empty(B * H * W, E, device="cuda", dtype=torch.half)
+    fn = lambda: ops.cfm_attention(qkv_t, kvp, bias, out, B, H, W, E, 8, 32 ** -0.5)
 elif which == "ln":
     M, C = 115200, 64
     x, gm, bt, out = rn(M, C), rn(C), rn(C), torch.empty(M, C, device="cuda", dtype=torch.half)
