@@ -246,6 +246,18 @@ int cffm_kmeans_update(const float* partials, int nsplit, const int* counts, flo
 /* x fp16 [rows, cols] -> xt fp16 [cols, rows_pad] (columns >= rows zero). */
 int cffm_transpose_f16(const void* x, int rows, int cols, void* xt, int rows_pad, void* stream);
 
+/* ---- test-time clip preprocessing (mmseg/datasets/pipelines/transforms.py:382-421 AlignedResize_clips, :1277-1297
+ * Normalize_clips; the arithmetic is mmcv 1.3.0 -> OpenCV).  Bit-exact with cv2 / mmcv. */
+
+/* cv2.resize(..., INTER_LINEAR) of N uint8 HWC 3-channel images [N,h,w,3] -> [N,H,W,3] (8-bit fixed-point path). */
+int cffm_resize_u8(const void* src, int N, int h, int w, void* dst, int H, int W, void* stream);
+
+/* The same resize (the identity when h == H and w == W) fused with mmcv.imnormalize and HWC -> CHW:
+ * out[n] (at out + n*out_stride floats) = fp32 [3,H,W], channel c = (pix[to_rgb ? 2-c : c] - mean3[c]) / std3[c]
+ * evaluated as float(double(float(x) - mean) * (1 / double(std))).  mean3 / std3 are HOST pointers. */
+int cffm_resize_normalize_u8(const void* src, int N, int h, int w, float* out, int64_t out_stride, int H, int W,
+                             const float* mean3, const float* std3, int to_rgb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

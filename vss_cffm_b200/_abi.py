@@ -44,6 +44,8 @@ SIGNATURES = {
     "cffm_cffa_pool": ([vp, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
     "cffm_cffa_pool_part": ([vp, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
     "cffm_cffa_pool_level": ([vp, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
+    "cffm_resize_u8": ([vp, i32, i32, i32, vp, i32, i32, vp], i32),
+    "cffm_resize_normalize_u8": ([vp, i32, i32, i32, vp, i64, i32, i32, vp, vp, i32, vp], i32),
     "cffm_kmeans_prepare": ([vp, vp, vp, vp, i32, i32, i32, vp], i32),
     "cffm_kmeans_assign": ([vp, i64, vp, i32, i32, i32, i32, vp, vp, vp, vp], i32),
     "cffm_kmeans_update": ([vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp], i32),
