@@ -257,6 +257,7 @@ def main():
     e2e_serial_ms = timed(step_e2e, args.steps)
     barrier()
     e2e_ms, e2e_api = e2e_serial_ms, "EncoderDecoder_clips.predict_labels(pinned host frames) + D2H of the int64 label maps"
+    e2e_u8, e2e_u8_ms = None, 0.0
     if graphed is not None:
         # streaming API: the H2D of batch i+1 and the D2H of batch i-1 overlap the kernels of batch i.  Every step still
         # copies its own frames from pinned host memory and reads its own labels back; the L2 flush runs INSIDE the
@@ -289,6 +290,21 @@ def main():
         e2e_api = ("ClipPipeline.submit(pinned host frames, pinned host labels): H2D / CUDA-graph replay / D2H on three "
                    "streams, 2 slots in flight; L2 flush inside the timed region")
         barrier()
+        # the same pipeline fed DECODED frames (uint8 BGR HWC, what the reference's LoadImageFromFile produces): resize /
+        # normalise / layout change on the GPU (vss_cffm_b200/preprocess.py), a quarter of the H2D bytes.  Reported beside
+        # the headline e2e (whose input is the fp32 tensor the reference model itself receives).
+        from vss_cffm_b200.preprocess import ClipPreprocessor
+        pre = ClipPreprocessor()
+        pipe = ClipPipeline(model, B, T, H, W, metas, preprocessor=pre, src_hw=(H, W))
+        g8 = torch.Generator().manual_seed(300 + rank)
+        hosts = [torch.randint(0, 256, (T, B, H, W, 3), dtype=torch.uint8, generator=g8).pin_memory() for _ in range(3)]
+        pipelined(3)
+        u8_ms = pipelined(args.steps)
+        e2e_u8 = {"value": None, "unit": UNIT, "ms_per_step": round(u8_ms / args.steps, 4), "h2d_bytes_per_step": B * T * 3 * H * W,
+                  "d2h_bytes_per_step": B * H * W * 8,
+                  "api": "ClipPipeline(preprocessor=ClipPreprocessor()).submit(pinned uint8 BGR HWC frames, pinned labels)"}
+        e2e_u8_ms = u8_ms
+        barrier()
 
     # per-kernel CUDA-event timing of the same step, launched eagerly (events cannot bracket nodes of a graph).  A spin
     # kernel is queued first so that the whole step (launches + events) is enqueued while the GPU is still busy: the
@@ -309,10 +325,10 @@ def main():
     breakdown = {k: {"launches_per_step": v[0] // ksteps, "us_per_step": round(1e3 * v[1] / ksteps, 1)}
                  for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])}
 
-    t = torch.tensor([total_ms, e2e_ms, e2e_serial_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, e2e_ms, e2e_serial_ms, e2e_u8_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, e2e_serial_ms = t.tolist()
+    total_ms, e2e_ms, e2e_serial_ms, e2e_u8_ms = t.tolist()
     frames = B * T * n_gpus * args.steps
     value = frames / (total_ms * 1e-3)
     e2e_value = frames / (e2e_ms * 1e-3)
@@ -385,6 +401,8 @@ def main():
                     "api": e2e_api,
                     "serial_value": round(frames / (e2e_serial_ms * 1e-3), 2),
                     "serial_api": "graph.load(pinned host frames) -> replay -> D2H labels, one step at a time (no overlap)"},
+            "e2e_from_uint8_frames": (dict(e2e_u8, value=round(frames / (e2e_u8_ms * 1e-3), 2), ms_per_step=round(e2e_u8_ms / args.steps, 4))
+                                      if e2e_u8 else None),
             "gpu_launches": launches,
             "launch_mode": "eager" if graphed is None else f"CUDA graph replay ({graphed.kernels_per_replay} kernel nodes per step)",
             "kernel_time_sum_ms_per_step": round(eager_ms / ksteps, 4),

@@ -98,3 +98,31 @@ def test_gpu_clip_preprocessor_matches_the_pipeline(pre):
         assert np.array_equal(metas[b]["scale_factor"], sf) and metas[b]["flip"] is False
     with pytest.raises(Exception):
         pre.resize_u8(torch.from_numpy(clips[0][0][None]), 480, 864)            # CPU tensor: no fallback
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_from_uint8_frames_equals_direct_call(pre):
+    """ClipPipeline fed decoded uint8 frames (preprocessing captured in the CUDA graph) == preprocess, then predict_labels."""
+    import vss_cffm_b200 as V
+    from vss_cffm_b200 import synth
+    from vss_cffm_b200.graph import ClipPipeline
+    torch.set_grad_enabled(False)
+    m = V.build_segmentor(V.model_cfg("b0"))
+    synth.fill_module(m, 5)
+    m = m.cuda().eval()
+    T, B, h, w = 4, 1, 90, 160
+    pp = pre.ClipPreprocessor(img_scale=(160, 90), size_divisor=32)
+    (_, _), (H, W) = pp.output_size(h, w)
+    assert (H, W) == (96, 160)
+    g = torch.Generator().manual_seed(9)
+    batches = [torch.randint(0, 256, (T, B, h, w, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(3)]
+    metas = pp.metas(B, h, w)
+    pipe = ClipPipeline(m, B, T, H, W, metas, rescale=False, preprocessor=pp, src_hw=(h, w))
+    outs = [torch.empty(B, H, W, dtype=torch.int64).pin_memory() for _ in range(3)]
+    for x, o in zip(batches, outs):
+        pipe.submit(x, o)
+    pipe.drain()
+    for x, o in zip(batches, outs):
+        frames = pp.run(x.cuda().view(T * B, h, w, 3), T, B)
+        ref = m.labels_from_frames(frames, metas, rescale=False)
+        assert torch.equal(ref.cpu(), o)

@@ -9,7 +9,10 @@ from . import _abi
 
 
 class GraphedClips:
-    def __init__(self, model, B, T, H, W, img_meta=None, rescale=True, head_kw=None, warmup=3, private_input=False):
+    def __init__(self, model, B, T, H, W, img_meta=None, rescale=True, head_kw=None, warmup=3, private_input=False,
+                 preprocessor=None, src_hw=None):
+        """``preprocessor`` (a ``ClipPreprocessor``) + ``src_hw``: the captured pass starts from a static uint8 BGR HWC
+        buffer ``self.frames_u8`` (T, B, h, w, 3) of decoded frames instead of the normalised fp32 frames."""
         dev = model._device()
         if dev.type != "cuda":
             raise _abi.CffmError("CUDA graphs need the model on a CUDA device")
@@ -21,17 +24,28 @@ class GraphedClips:
             self.frames = torch.empty(T, B, 3, H, W, dtype=torch.float32, device=dev)
         else:
             self.frames = model._ws.get("frames", (T, B, 3, H, W), torch.float32, device=dev)   # static input buffer
+        self.frames_u8 = None
+        if preprocessor is not None:
+            h, w = src_hw
+            assert preprocessor.output_size(h, w)[1] == (H, W), "preprocessor output size != model input size"
+            self.frames_u8 = torch.zeros(T, B, h, w, 3, dtype=torch.uint8, device=dev)
+
+        def run_pass():
+            if preprocessor is not None:
+                preprocessor.run(self.frames_u8.view(T * B, *self.frames_u8.shape[2:]), T, B, out=self.frames)
+            return model.labels_from_frames(self.frames, self.meta, rescale, **head_kw)
+
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                            # plans, workspaces, func attributes: all set here
             for _ in range(warmup):
-                model.labels_from_frames(self.frames, self.meta, rescale, **head_kw)
+                run_pass()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         n0 = _abi.n_launches
         with torch.cuda.graph(self.graph):
-            self.labels = model.labels_from_frames(self.frames, self.meta, rescale, **head_kw)
+            self.labels = run_pass()
         self.kernels_per_replay = _abi.n_launches - n0
 
     def load(self, imgs):
@@ -62,12 +76,15 @@ class ClipPipeline:
         pipe.wait(tickets[-1])                                                   # or pipe.drain()
     """
 
-    def __init__(self, model, B, T, H, W, img_meta=None, rescale=True, head_kw=None, depth=2):
+    def __init__(self, model, B, T, H, W, img_meta=None, rescale=True, head_kw=None, depth=2, preprocessor=None, src_hw=None):
+        """With ``preprocessor`` / ``src_hw`` the pipeline is fed decoded uint8 BGR HWC frames (T, B, h, w, 3): a quarter of
+        the H2D bytes, and the resize / normalise / layout change run on the GPU inside the captured pass."""
         dev = model._device()
         self.dev, self.depth, self.T = dev, depth, T
         self.slots = []
         for s in range(depth):
-            g = GraphedClips(model, B, T, H, W, img_meta, rescale, head_kw, warmup=3 if s == 0 else 1, private_input=True)
+            g = GraphedClips(model, B, T, H, W, img_meta, rescale, head_kw, warmup=3 if s == 0 else 1, private_input=True,
+                             preprocessor=preprocessor, src_hw=src_hw)
             self.slots.append(dict(g=g, h2d=torch.cuda.Event(), done=torch.cuda.Event(), d2h=torch.cuda.Event(), used=False))
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
         self.n = 0
@@ -83,11 +100,12 @@ class ClipPipeline:
         with torch.cuda.stream(self.s_in):
             if sl["used"]:
                 self.s_in.wait_event(sl["done"])                 # the previous batch in this slot has been consumed
+            dst = g.frames if g.frames_u8 is None else g.frames_u8
             if isinstance(imgs, (list, tuple)):
                 for t, f in enumerate(imgs):
-                    g.frames[t].copy_(f, non_blocking=True)
+                    dst[t].copy_(f, non_blocking=True)
             else:
-                g.frames.copy_(imgs, non_blocking=True)
+                dst.copy_(imgs, non_blocking=True)
             sl["h2d"].record(self.s_in)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(sl["h2d"])

@@ -74,20 +74,28 @@ class ClipPreprocessor:
         d = self.size_divisor
         return (rh, rw), (int(np.ceil(rh / d)) * d, int(np.ceil(rw / d)) * d)
 
-    def __call__(self, clips, filenames=None, out=None):
-        _abi.require_device()
-        B, T = len(clips), len(clips[0])
-        h, w = clips[0][0].shape[:2]
+    def run(self, x, T, B, out=None):
+        """Device part (no host work, CUDA-graph capturable): x uint8 (T*B, h, w, 3) CUDA, frame-major -> (T,B,3,H,W) fp32."""
+        h, w = x.shape[1:3]
         (rh, rw), (H, W) = self.output_size(h, w)
-        x = _as_u8_batch([clips[b][t] for t in range(T) for b in range(B)], self.device)   # frame-major
         if (rh, rw) != (h, w):
             x = resize_u8(x, rh, rw)                             # mmcv.imrescale (transforms.py:399-400)
         if out is None:
             out = torch.empty(T, B, 3, H, W, dtype=torch.float32, device=x.device)
         resize_normalize(x, H, W, self.mean, self.std, self.to_rgb, out=out.view(T * B, 3, H, W))   # _align + Normalize_clips
+        return out
+
+    def metas(self, B, h, w, filenames=None):
+        (_, _), (H, W) = self.output_size(h, w)
         sf = np.array([W / w, H / h, W / w, H / h], dtype=np.float32)
-        metas = [dict(ori_shape=(h, w, 3), img_shape=(H, W, 3), pad_shape=(H, W, 3), scale_factor=sf, flip=False,
-                      keep_ratio=True, filename=(filenames[b] if filenames else f"data/video{b}/origin/00000000.jpg"),
-                      img_norm_cfg=dict(mean=np.array(self.mean, np.float32), std=np.array(self.std, np.float32), to_rgb=self.to_rgb))
-                 for b in range(B)]
-        return out, metas
+        return [dict(ori_shape=(h, w, 3), img_shape=(H, W, 3), pad_shape=(H, W, 3), scale_factor=sf, flip=False,
+                     keep_ratio=True, filename=(filenames[b] if filenames else f"data/video{b}/origin/00000000.jpg"),
+                     img_norm_cfg=dict(mean=np.array(self.mean, np.float32), std=np.array(self.std, np.float32), to_rgb=self.to_rgb))
+                for b in range(B)]
+
+    def __call__(self, clips, filenames=None, out=None):
+        _abi.require_device()
+        B, T = len(clips), len(clips[0])
+        h, w = clips[0][0].shape[:2]
+        x = _as_u8_batch([clips[b][t] for t in range(T) for b in range(B)], self.device)   # frame-major
+        return self.run(x, T, B, out), self.metas(B, h, w, filenames)
