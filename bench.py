@@ -306,6 +306,23 @@ def main():
         e2e_u8_ms = u8_ms
         barrier()
 
+    # ---- streaming with temporal re-use (vss_cffm_b200/streaming.py; not the headline: the clips of the headline metric
+    # are independent).  One step = the next frame of each of B videos; labels are bit-identical to the stateless path.
+    streaming = None
+    if not frames_mode:
+        from vss_cffm_b200.streaming import VideoStream
+        vs = VideoStream(model, B, graph=True)
+        vframes = [imgs_dev[t % T] for t in range(8)]
+        for t in range(2 * vs.history + 2):                      # fill the history and capture the per-residue graphs
+            vs.push(vframes[t % 8])
+        torch.cuda.synchronize()
+        sm = timed(lambda: vs.push(vframes[vs.i % 8]), args.steps)
+        streaming = {"value": round(B * args.steps / (sm * 1e-3), 2), "unit": "target-frames/s", "ms_per_step": round(sm / args.steps, 4),
+                     "streams": B, "stateless_equivalent": None,
+                     "note": "VideoStream.push: every frame is encoded once and its reference K/V cached; the stateless path "
+                             "segments one target per T=4 clip-frames"}
+    barrier()
+
     # per-kernel CUDA-event timing of the same step, launched eagerly (events cannot bracket nodes of a graph).  A spin
     # kernel is queued first so that the whole step (launches + events) is enqueued while the GPU is still busy: the
     # events then measure kernel durations, not the host's launch gaps.
@@ -403,6 +420,7 @@ def main():
                     "serial_api": "graph.load(pinned host frames) -> replay -> D2H labels, one step at a time (no overlap)"},
             "e2e_from_uint8_frames": (dict(e2e_u8, value=round(frames / (e2e_u8_ms * 1e-3), 2), ms_per_step=round(e2e_u8_ms / args.steps, 4))
                                       if e2e_u8 else None),
+            "streaming": (dict(streaming, stateless_equivalent=round(value / T, 2)) if streaming else None),
             "gpu_launches": launches,
             "launch_mode": "eager" if graphed is None else f"CUDA graph replay ({graphed.kernels_per_replay} kernel nodes per step)",
             "kernel_time_sum_ms_per_step": round(eager_ms / ksteps, 4),
