@@ -76,6 +76,14 @@ int cffm_gemm_f16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, con
                      const float* ln_gamma, const float* ln_beta, float ln_eps, void* ln_out_f16,
                      int64_t ldln, int M, int N, int K, void* stream);
 
+/* The same with TWO chained LayerNorms (OverlapPatchEmbed.norm, mix_transformer.py:198, followed by the first block's
+ * norm1, :154) and no residual: x = A.W^T + bias;  y = LayerNorm(x; gamma1, beta1, eps1) -> out_f32 [M,N];
+ * LayerNorm(y; gamma2, beta2, eps2) -> ln_out_f16 [M,N].  N <= 128. */
+int cffm_gemm_f16_ln_chain(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* out_f32,
+                           int64_t ldo32, const float* gamma1, const float* beta1, float eps1, const float* gamma2,
+                           const float* beta2, float eps2, void* ln_out_f16, int64_t ldln, int M, int N, int K,
+                           void* stream);
+
 /* Split-K GEMM for the few-tile / long-K convolutions of the path (spatial-reduction conv
  * mix_transformer.py:76,101-102 with K = sr*sr*C up to 4096; patch embeds of stages 3-4 with K = 9*C):
  * split s covers a contiguous range of 64-wide k-blocks and writes its fp32 partial product to

@@ -431,6 +431,24 @@ def test_gemm_with_fused_layernorm(ops, M, N, K):
     assert ops.gemm_ln_supported(128) and not ops.gemm_ln_supported(320)
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 152), (300, 128, 576), (4100, 32, 152), (129, 64, 256), (77, 8, 64)])
+def test_gemm_with_two_chained_layernorms(ops, M, N, K):
+    """y = LN1(A W^T + bias) in fp32 and LN2(y) in fp16 from ONE kernel (patch-embed conv + norm + first norm1)."""
+    a = h16(synth.synth_array((M, K), 51)).cuda()
+    w = h16(synth.synth_array((N, K), 52, scale=K ** -0.5)).cuda()
+    bias = synth.synth_array((N,), 53).cuda()
+    g1, b1 = (synth.synth_array((N,), 54) * 0.1 + 1).cuda(), (synth.synth_array((N,), 55) * 0.1).cuda()
+    g2, b2 = (synth.synth_array((N,), 56) * 0.1 + 1).cuda(), (synth.synth_array((N,), 57) * 0.1).cuda()
+    x = a.double() @ w.double().t() + bias.double()
+    y_ref = F.layer_norm(x, (N,), g1.double(), b1.double(), 1e-5)
+    z_ref = F.layer_norm(y_ref, (N,), g2.double(), b2.double(), 1e-6)
+    y = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    z = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    ops.gemm_ln_chain(a.half(), w.half(), bias, y, g1, b1, 1e-5, g2, b2, 1e-6, z)
+    check(y, y_ref, 2e-4, "chain: first norm")        # LN of fp16-product sums: the GEMM's own rounding passes through rstd
+    check(z, z_ref, REL16, "chain: second norm")
+
+
 @pytest.mark.parametrize("M,N,K", [(1800, 64, 4096), (450, 512, 2880), (1800, 128, 2048), (225, 32, 2048), (300, 64, 512)])
 def test_splitk_gemm_and_summing_layernorm(ops, M, N, K):
     """Split-K partial products + LayerNorm(sum + bias) == conv-as-GEMM followed by LayerNorm (mix_transformer.py:101-103)."""

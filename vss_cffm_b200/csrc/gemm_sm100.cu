@@ -44,6 +44,11 @@ struct Epilogue {
   float ln_eps;
   __half* ln_out16;
   int64_t ldln;
+  // optional SECOND LayerNorm chained on the first (patch-embed norm -> first block's norm1): out32 then receives
+  // y = LN(x; ln_gamma, ln_beta) instead of x, and ln_out16 receives LN(y; ln2_gamma, ln2_beta)
+  const float* ln2_gamma;
+  const float* ln2_beta;
+  float ln2_eps;
   // split-K: tile t covers k-blocks [split * kb_per, +kb_per) and writes its partial sums to out32 + split * split_stride
   int splits;
   int kb_per;
@@ -83,13 +88,13 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, accumulator stage = tile parity
 //   warps 2..17 epilogue: tcgen05.ld (thread = row) -> per-warp smem transpose -> row-contiguous
 //               global accesses for residual / fp32 / fp16 (+ optional fused LayerNorm); overlaps the mainloop
-template <int BN, bool F16_ONLY, bool LN, int EW>
+template <int BN, bool F16_ONLY, int LN, int EW>   // LN: 0 none, 1 fused LayerNorm, 2 two chained LayerNorms
 __global__ void __launch_bounds__(Cfg<BN, EW, F16_ONLY>::THREADS, Cfg<BN, EW, F16_ONLY>::MIN_CTAS)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO, const Epilogue ep, const int M, const int N, const int K, const int n_tiles_n,
                     const int n_tiles) {
   using C = Cfg<BN, EW, F16_ONLY>;
-  static_assert(!LN || EW == 16, "the fused LayerNorm lives in the 16-warp kernel");
+  static_assert(LN == 0 || EW == 16, "the fused LayerNorm lives in the 16-warp kernel");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -293,7 +298,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (ep.residual != nullptr) { a.x += r4[i].x; a.y += r4[i].y; a.z += r4[i].z; a.w += r4[i].w; }
         av[i] = a;
         if (row < M && cvalid && !(dbg & 1)) {
-          if (ep.out32 != nullptr)
+          if (ep.out32 != nullptr && LN != 2)
             *reinterpret_cast<float4*>(ep.out32 + split * ep.split_stride + static_cast<int64_t>(row) * ep.ldo32 + col) = a;
           if (ep.out16 != nullptr) {
             uint2 h;
@@ -304,7 +309,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       __syncwarp();                                            // transpose buffer is re-used by the next tile
-      if constexpr (LN) {
+      if constexpr (LN != 0) {
         // ---- fused LayerNorm over the N (<= BN) columns of each row.  A row lives in 8 lanes (same rsub) of each
         // of the BN/32 warps of this (team, quarter): two-pass statistics, partial sums exchanged through shared
         // memory with one named barrier per (team, quarter).
@@ -313,54 +318,84 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float* bsum = lnbuf + ((tm * 4 + wq) * 2 + 0) * (4 * 32);      // [cg][32 rows]
         float* bsq = lnbuf + ((tm * 4 + wq) * 2 + 1) * (4 * 32);
         const int bar_id = 1 + tm * 4 + wq;
-        float st[8], mean[8];
+        float mean[8];
+        auto row_stats = [&]() {                               // mean[] of the rows held in av[]; leaves the centred sums in bsq
+          float st[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float sacc = cvalid ? (av[i].x + av[i].y) + (av[i].z + av[i].w) : 0.f;
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
-          st[i] = sacc;
-        }
-        if ((lane & 7) == 0) {
+          for (int i = 0; i < 8; ++i) {
+            float sacc = cvalid ? (av[i].x + av[i].y) + (av[i].z + av[i].w) : 0.f;
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+            st[i] = sacc;
+          }
+          if ((lane & 7) == 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bsum[cg * 32 + rsub + 4 * i] = st[i];
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NG * 32) : "memory");
+            for (int i = 0; i < 8; ++i) bsum[cg * 32 + rsub + 4 * i] = st[i];
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NG * 32) : "memory");
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 8; ++i) {
+            float tot = 0.f;
+#pragma unroll
+            for (int gq = 0; gq < NG; ++gq) tot += bsum[gq * 32 + rsub + 4 * i];
+            mean[i] = tot * invN;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float dx = av[i].x - mean[i], dy = av[i].y - mean[i], dz = av[i].z - mean[i], dw = av[i].w - mean[i];
+            float sacc = cvalid ? (dx * dx + dy * dy) + (dz * dz + dw * dw) : 0.f;
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+            st[i] = sacc;
+          }
+          if ((lane & 7) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bsq[cg * 32 + rsub + 4 * i] = st[i];
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NG * 32) : "memory");
+        };
+        auto row_rstd = [&](int i, float eps) {
           float tot = 0.f;
 #pragma unroll
-          for (int gq = 0; gq < NG; ++gq) tot += bsum[gq * 32 + rsub + 4 * i];
-          mean[i] = tot * invN;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float dx = av[i].x - mean[i], dy = av[i].y - mean[i], dz = av[i].z - mean[i], dw = av[i].w - mean[i];
-          float sacc = cvalid ? (dx * dx + dy * dy) + (dz * dz + dw * dw) : 0.f;
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
-          st[i] = sacc;
-        }
-        if ((lane & 7) == 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) bsq[cg * 32 + rsub + 4 * i] = st[i];
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NG * 32) : "memory");
+          for (int gq = 0; gq < NG; ++gq) tot += bsq[gq * 32 + rsub + 4 * i];
+          return rsqrtf(tot * invN + eps);
+        };
+        row_stats();
+        constexpr bool chain = LN == 2;
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), be4 = g4;
         if (cvalid) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + col));
-          const float4 be4 = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + col));
+          g4 = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + col));
+          be4 = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + col));
+        }
+        if constexpr (chain) {
+          // y = LN1(x) is the fp32 output; the second LayerNorm runs on y without leaving the registers
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = wrow0 + rsub + 4 * i;
-            float tot = 0.f;
+            const float rs = row_rstd(i, ep.ln_eps);
+            av[i].x = (av[i].x - mean[i]) * rs * g4.x + be4.x; av[i].y = (av[i].y - mean[i]) * rs * g4.y + be4.y;
+            av[i].z = (av[i].z - mean[i]) * rs * g4.z + be4.z; av[i].w = (av[i].w - mean[i]) * rs * g4.w + be4.w;
+            if (row < M && cvalid && ep.out32 != nullptr && !(dbg & 1))
+              *reinterpret_cast<float4*>(ep.out32 + static_cast<int64_t>(row) * ep.ldo32 + col) = av[i];
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NG * 32) : "memory");   // everyone has read bsq of the first norm
+          row_stats();
+          if (cvalid) {
+            g4 = __ldg(reinterpret_cast<const float4*>(ep.ln2_gamma + col));
+            be4 = __ldg(reinterpret_cast<const float4*>(ep.ln2_beta + col));
+          }
+        }
+        const float eps_out = chain ? ep.ln2_eps : ep.ln_eps;
+        if (cvalid) {
 #pragma unroll
-            for (int gq = 0; gq < NG; ++gq) tot += bsq[gq * 32 + rsub + 4 * i];
-            const float rstd = rsqrtf(tot * invN + ep.ln_eps);
+          for (int i = 0; i < 8; ++i) {
+            const int row = wrow0 + rsub + 4 * i;
+            const float rs = row_rstd(i, eps_out);
             uint2 h;
-            h.x = pack_half2((av[i].x - mean[i]) * rstd * g4.x + be4.x, (av[i].y - mean[i]) * rstd * g4.y + be4.y);
-            h.y = pack_half2((av[i].z - mean[i]) * rstd * g4.z + be4.z, (av[i].w - mean[i]) * rstd * g4.w + be4.w);
+            h.x = pack_half2((av[i].x - mean[i]) * rs * g4.x + be4.x, (av[i].y - mean[i]) * rs * g4.y + be4.y);
+            h.y = pack_half2((av[i].z - mean[i]) * rs * g4.z + be4.z, (av[i].w - mean[i]) * rs * g4.w + be4.w);
             if (row < M && !(dbg & 1)) *reinterpret_cast<uint2*>(ep.ln_out16 + static_cast<int64_t>(row) * ep.ldln + col) = h;
           }
         }
@@ -483,7 +518,7 @@ static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_
 
 namespace {
 
-template <int BN, bool F16_ONLY, bool LN = false, int EW = 16>
+template <int BN, bool F16_ONLY, int LN = 0, int EW = 16>
 int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const Epilogue& ep, int M, int N, int K,
                    cudaStream_t st) {
   using C = Cfg<BN, EW, F16_ONLY>;
@@ -543,7 +578,7 @@ extern "C" int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t 
                CFFM_E_BADARG, "gemm: bad output/residual stride");
   CFFM_REQUIRE(act >= CFFM_ACT_NONE && act <= CFFM_ACT_RELU, CFFM_E_BADARG, "gemm: bad act %d", act);
   Epilogue ep{bias, residual, ldr, static_cast<__half*>(out_f16), ldo16, out_f32, ldo32, act, nullptr, nullptr, 0.f, nullptr, 0,
-              1, (K + BLOCK_K - 1) / BLOCK_K, 0};
+              nullptr, nullptr, 0.f, 1, (K + BLOCK_K - 1) / BLOCK_K, 0};
   if (const char* dbg = getenv("CFFM_GEMM_DEBUG")) ep.act |= atoi(dbg) << 8;   // bring-up experiments only (tools/gemm_probe.py)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (impl == CFFM_GEMM_CHECK) {
@@ -556,8 +591,8 @@ extern "C" int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t 
   const bool f16_only = out_f16 != nullptr && out_f32 == nullptr && residual == nullptr;
   const int tiles64 = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + 63) / 64);
   if (tiles64 <= small_gemm_max_tiles()) {
-    return f16_only ? launch_tcgen05<64, true, false, 8>(A, lda, W, ldw, ep, M, N, K, st)
-                    : launch_tcgen05<64, false, false, 8>(A, lda, W, ldw, ep, M, N, K, st);
+    return f16_only ? launch_tcgen05<64, true, 0, 8>(A, lda, W, ldw, ep, M, N, K, st)
+                    : launch_tcgen05<64, false, 0, 8>(A, lda, W, ldw, ep, M, N, K, st);
   }
   const bool wide = N % 128 == 0 || (N % 64 != 0 && N > 64);   // 128-wide tiles halve the A re-reads of the big GEMMs
   if (f16_only) {
@@ -568,10 +603,10 @@ extern "C" int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t 
               : launch_tcgen05<64, false>(A, lda, W, ldw, ep, M, N, K, st);
 }
 
-extern "C" int cffm_gemm_f16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
-                                const float* residual, int64_t ldr, float* out_f32, int64_t ldo32, const float* ln_gamma,
-                                const float* ln_beta, float ln_eps, void* ln_out_f16, int64_t ldln, int M, int N, int K,
-                                void* stream) {
+static int gemm_ln_impl(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
+                       int64_t ldr, float* out_f32, int64_t ldo32, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                       const float* ln2_gamma, const float* ln2_beta, float ln2_eps, void* ln_out_f16, int64_t ldln, int M,
+                       int N, int K, void* stream) {
   using namespace cffm;
   CFFM_REQUIRE(A && W && ln_gamma && ln_beta && ln_out_f16, CFFM_E_BADARG, "gemm_ln: null operand");
   CFFM_REQUIRE(M > 0 && N > 0 && K > 0, CFFM_E_BADARG, "gemm_ln: non-positive size M=%d N=%d K=%d", M, N, K);
@@ -585,10 +620,30 @@ extern "C" int cffm_gemm_f16_ln(const void* A, int64_t lda, const void* W, int64
                    ldln >= N,
                CFFM_E_BADARG, "gemm_ln: bad output/residual stride");
   Epilogue ep{bias, residual, ldr, nullptr, 0, out_f32, ldo32, CFFM_ACT_NONE, ln_gamma, ln_beta, ln_eps,
-              static_cast<__half*>(ln_out_f16), ldln, 1, (K + BLOCK_K - 1) / BLOCK_K, 0};
+              static_cast<__half*>(ln_out_f16), ldln, ln2_gamma, ln2_beta, ln2_eps, 1, (K + BLOCK_K - 1) / BLOCK_K, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return N > 64 ? launch_tcgen05<128, false, true>(A, lda, W, ldw, ep, M, N, K, st)
-                : launch_tcgen05<64, false, true>(A, lda, W, ldw, ep, M, N, K, st);
+  if (ln2_gamma != nullptr)
+    return N > 64 ? launch_tcgen05<128, false, 2>(A, lda, W, ldw, ep, M, N, K, st) : launch_tcgen05<64, false, 2>(A, lda, W, ldw, ep, M, N, K, st);
+  return N > 64 ? launch_tcgen05<128, false, 1>(A, lda, W, ldw, ep, M, N, K, st) : launch_tcgen05<64, false, 1>(A, lda, W, ldw, ep, M, N, K, st);
+}
+
+extern "C" int cffm_gemm_f16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                const float* residual, int64_t ldr, float* out_f32, int64_t ldo32, const float* ln_gamma,
+                                const float* ln_beta, float ln_eps, void* ln_out_f16, int64_t ldln, int M, int N, int K,
+                                void* stream) {
+  return gemm_ln_impl(A, lda, W, ldw, bias, residual, ldr, out_f32, ldo32, ln_gamma, ln_beta, ln_eps, nullptr, nullptr, 0.f,
+                      ln_out_f16, ldln, M, N, K, stream);
+}
+
+extern "C" int cffm_gemm_f16_ln_chain(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* out_f32,
+                                      int64_t ldo32, const float* gamma1, const float* beta1, float eps1, const float* gamma2,
+                                      const float* beta2, float eps2, void* ln_out_f16, int64_t ldln, int M, int N, int K,
+                                      void* stream) {
+  using namespace cffm;
+  CFFM_REQUIRE(gamma2 && beta2 && out_f32, CFFM_E_BADARG, "gemm_ln_chain: null operand");
+  CFFM_REQUIRE(aligned16(gamma2) && aligned16(beta2), CFFM_E_BADARG, "gemm_ln_chain: misaligned pointer");
+  return gemm_ln_impl(A, lda, W, ldw, bias, nullptr, 0, out_f32, ldo32, gamma1, beta1, eps1, gamma2, beta2, eps2, ln_out_f16, ldln,
+                      M, N, K, stream);
 }
 
 extern "C" int cffm_gemm_f16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* partials, int M, int N,
@@ -603,11 +658,11 @@ extern "C" int cffm_gemm_f16_splitk(const void* A, int64_t lda, const void* W, i
   CFFM_REQUIRE(splits <= num_kb, CFFM_E_BADARG, "gemm_splitk: %d splits for %d k-blocks", splits, num_kb);
   const int kb_per = (num_kb + splits - 1) / splits;
   CFFM_REQUIRE((splits - 1) * kb_per < num_kb, CFFM_E_BADARG, "gemm_splitk: empty split (use cffm_splitk_plan)");
-  Epilogue ep{nullptr, nullptr, 0, nullptr, 0, partials, N, CFFM_ACT_NONE, nullptr, nullptr, 0.f, nullptr, 0,
+  Epilogue ep{nullptr, nullptr, 0, nullptr, 0, partials, N, CFFM_ACT_NONE, nullptr, nullptr, 0.f, nullptr, 0, nullptr, nullptr, 0.f,
               splits, kb_per, static_cast<int64_t>(M) * N};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int tiles64 = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + 63) / 64) * splits;
-  if (tiles64 <= small_gemm_max_tiles()) return launch_tcgen05<64, false, false, 8>(A, lda, W, ldw, ep, M, N, K, st);
+  if (tiles64 <= small_gemm_max_tiles()) return launch_tcgen05<64, false, 0, 8>(A, lda, W, ldw, ep, M, N, K, st);
   const bool wide = N % 128 == 0 || (N % 64 != 0 && N > 64);
   return wide ? launch_tcgen05<128, false>(A, lda, W, ldw, ep, M, N, K, st) : launch_tcgen05<64, false>(A, lda, W, ldw, ep, M, N, K, st);
 }

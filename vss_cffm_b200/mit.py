@@ -205,6 +205,8 @@ class MixVisionTransformer(nn.Module):
             if S > 1:
                 ops.gemm_splitk(col, st["w"], pe32)
                 ops.layernorm_chain(pe32, st["b"], st["ng"], st["nb"], st["eps"], xres, b0["n1g"], b0["n1b"], b0["n1eps"], xn)
+            elif C <= 128:                                       # both norms ride in the GEMM epilogue (one tile spans the row)
+                ops.gemm_ln_chain(col, st["w"], st["b"], xres, st["ng"], st["nb"], st["eps"], b0["n1g"], b0["n1b"], b0["n1eps"], xn)
             else:
                 ops.gemm(col, st["w"], bias=st["b"], out32=pe32[0])
                 ops.layernorm_chain(pe32, None, st["ng"], st["nb"], st["eps"], xres, b0["n1g"], b0["n1b"], b0["n1eps"], xn)

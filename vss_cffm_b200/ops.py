@@ -73,6 +73,20 @@ def gemm_ln(a, w, bias, residual, out32, ln_gamma, ln_beta, ln_eps, ln_out16):
               _ptr(ln_gamma), _ptr(ln_beta), float(ln_eps), _ptr(ln_out16), _ld(ln_out16), M, N, K, _stream())
 
 
+def gemm_ln_chain(a, w, bias, out32, g1, b1, eps1, g2, b2, eps2, ln_out16):
+    """y = LayerNorm(a @ w.T + bias; g1, b1) -> out32;  LayerNorm(y; g2, b2) -> ln_out16.  N <= 128."""
+    _chk(a, _H, "gemm_ln_chain.a"); _chk(w, _H, "gemm_ln_chain.w"); _chk(out32, _F, "gemm_ln_chain.out32")
+    _chk(ln_out16, _H, "gemm_ln_chain.ln_out16")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and tuple(out32.shape) == (M, N) == tuple(ln_out16.shape) and N <= 128
+    for t in (bias, g1, b1, g2, b2):
+        if t is not None:
+            _chk(t, _F, "gemm_ln_chain.vector"); assert t.numel() == N
+    _abi.call("cffm_gemm_f16_ln_chain", _ptr(a), _ld(a), _ptr(w), _ld(w), _ptr(bias), _ptr(out32), _ld(out32), _ptr(g1), _ptr(b1),
+              float(eps1), _ptr(g2), _ptr(b2), float(eps2), _ptr(ln_out16), _ld(ln_out16), M, N, K, _stream())
+
+
 def splitk_plan(M, N, K):
     """Number of K splits that fills the SMs for a few-tile / long-K GEMM (1 = do not split)."""
     return int(_abi.load().cffm_splitk_plan(M, N, K))
