@@ -112,8 +112,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-  const int dbg = ep.act >> 8;                                 // 0 in production
-  const int act = ep.act & 0xff;
+  const int act = ep.act;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -150,11 +149,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb, ++g) {
           const uint32_t s = g % C::STAGES, ph = (g / C::STAGES) & 1u;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1u);              // slot free (passes on the first round)
-          if (dbg & 4) {                                       // probe: W only
-            ptx::mbar_arrive_expect_tx(&full_bar[s], C::W_STAGE_BYTES);
-            ptx::tma_load_2d(sW + s * C::W_STAGE_BYTES, &tmW, &full_bar[s], kb * BLOCK_K, n0);
-            continue;
-          }
           ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
           ptx::tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BLOCK_K, m0);
           ptx::tma_load_2d(sW + s * C::W_STAGE_BYTES, &tmW, &full_bar[s], kb * BLOCK_K, n0);
@@ -226,7 +220,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);     // registers hold the chunk: MMA may reuse the stage
-        if (dbg & 2) continue;                                 // probe: no epilogue work at all
         // bias + activation in the thread = row layout (bias is warp-uniform: broadcast LDS), pack to fp16 and stage the
         // warp's 32 x 32 chunk as [32 rows][64 B] in the 64-byte TMA swizzle (16-byte piece j of row r sits at
         // j ^ ((r >> 1) & 3): the 8 lanes of a store phase hit 8 distinct 16-byte bank groups).  One lane then hands the
@@ -251,7 +244,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         ptx::fence_proxy_async();                              // generic-proxy writes -> visible to the TMA (async proxy)
         __syncwarp();
-        if (lane == 0 && wcol0 < N && wrow0 < M && !(dbg & 1)) {
+        if (lane == 0 && wcol0 < N && wrow0 < M) {
           ptx::tma_store_2d(&tmO, stg8, wcol0, wrow0);
           ptx::bulk_commit();
         }
@@ -278,7 +271,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-      if (dbg & 2) continue;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) =
@@ -297,7 +289,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (ep.residual != nullptr) { a.x += r4[i].x; a.y += r4[i].y; a.z += r4[i].z; a.w += r4[i].w; }
         av[i] = a;
-        if (row < M && cvalid && !(dbg & 1)) {
+        if (row < M && cvalid) {
           if (ep.out32 != nullptr && LN != 2)
             *reinterpret_cast<float4*>(ep.out32 + split * ep.split_stride + static_cast<int64_t>(row) * ep.ldo32 + col) = a;
           if (ep.out16 != nullptr) {
@@ -377,7 +369,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float rs = row_rstd(i, ep.ln_eps);
             av[i].x = (av[i].x - mean[i]) * rs * g4.x + be4.x; av[i].y = (av[i].y - mean[i]) * rs * g4.y + be4.y;
             av[i].z = (av[i].z - mean[i]) * rs * g4.z + be4.z; av[i].w = (av[i].w - mean[i]) * rs * g4.w + be4.w;
-            if (row < M && cvalid && ep.out32 != nullptr && !(dbg & 1))
+            if (row < M && cvalid && ep.out32 != nullptr)
               *reinterpret_cast<float4*>(ep.out32 + static_cast<int64_t>(row) * ep.ldo32 + col) = av[i];
           }
           asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NG * 32) : "memory");   // everyone has read bsq of the first norm
@@ -396,7 +388,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint2 h;
             h.x = pack_half2((av[i].x - mean[i]) * rs * g4.x + be4.x, (av[i].y - mean[i]) * rs * g4.y + be4.y);
             h.y = pack_half2((av[i].z - mean[i]) * rs * g4.z + be4.z, (av[i].w - mean[i]) * rs * g4.w + be4.w);
-            if (row < M && !(dbg & 1)) *reinterpret_cast<uint2*>(ep.ln_out16 + static_cast<int64_t>(row) * ep.ldln + col) = h;
+            if (row < M) *reinterpret_cast<uint2*>(ep.ln_out16 + static_cast<int64_t>(row) * ep.ldln + col) = h;
           }
         }
       }
@@ -579,7 +571,6 @@ extern "C" int cffm_gemm_f16(const void* A, int64_t lda, const void* W, int64_t 
   CFFM_REQUIRE(act >= CFFM_ACT_NONE && act <= CFFM_ACT_RELU, CFFM_E_BADARG, "gemm: bad act %d", act);
   Epilogue ep{bias, residual, ldr, static_cast<__half*>(out_f16), ldo16, out_f32, ldo32, act, nullptr, nullptr, 0.f, nullptr, 0,
               nullptr, nullptr, 0.f, 1, (K + BLOCK_K - 1) / BLOCK_K, 0};
-  if (const char* dbg = getenv("CFFM_GEMM_DEBUG")) ep.act |= atoi(dbg) << 8;   // bring-up experiments only (tools/gemm_probe.py)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (impl == CFFM_GEMM_CHECK) {
     dim3 grid((N + CK_T - 1) / CK_T, (M + CK_T - 1) / CK_T);
