@@ -6,7 +6,7 @@ BASELINE size (480x480, T=4, B=2).
 Tolerances.  The GPU path computes with fp16 operands / fp32 accumulation and an fp32 residual
 stream; the reference is fp32 throughout.  north_star's bar is 1e-3 relative for the head on
 identical inputs; stacked stages accumulate independent fp16 roundings, so the bars are
-  head / CFFM blocks / CFFM++ branch (identical fp16-representable inputs): 3e-3 of the output scale
+  head / CFFM blocks / CFFM++ branch (identical fp16-representable inputs): 1e-3 of the output scale (the north_star bar)
   MiT backbone, 8+ blocks deep                                            : 1e-2 of the output scale
   end to end                                                              : 1e-2, labels >= 99 % equal
 measured as max|gpu - ref| / max|ref|; the achieved values are printed (-s) and logged in DESIGN.md."""
@@ -73,7 +73,7 @@ def test_cffm_blocks_vs_reference_golden(golden_dir):
     got = _run_cffm_blocks(head, x)
     e = rel_err(got, torch.from_numpy(g["target"]).permute(1, 2, 0))
     print(f"BasicLayer3d3 depth 2: rel err {e:.2e}")
-    assert e <= 3e-3, e
+    assert e <= 1e-3, e                                                      # the north_star bar: 1e-3 relative, fp16
 
 
 def _run_cffm_blocks(head, x):
@@ -139,7 +139,7 @@ def test_head_vs_oracle_identical_inputs(golden_dir):
     got = head.forward_test([f.cuda() for f in feats], None, None, B, T)          # clip-major input order
     e = rel_err(got, ref)
     print(f"CFFM head (depth 2) on identical inputs: logits rel err {e:.2e}")
-    assert e <= 3e-3, e
+    assert e <= 1e-3, e                                                      # the north_star bar: 1e-3 relative, fp16
     # frame-major feed gives the same result bit for bit
     fm = [f.view(B, T, *f.shape[1:]).transpose(0, 1).reshape(f.shape).cuda() for f in feats]
     got_fm = head.forward_test(fm, None, None, B, T, frame_major=True)
@@ -160,7 +160,7 @@ def test_head_early_return(golden_dir):
     got = head.forward_test([f.cuda() for f in feats], None, None, B, T)
     e = rel_err(got, ref)
     print(f"early-return head: rel err {e:.2e}")
-    assert e <= 3e-3, e
+    assert e <= 1e-3, e                                                      # the north_star bar: 1e-3 relative, fp16
 
 
 def test_cffmpp_cluster_branch_vs_reference_golden(golden_dir):
@@ -184,7 +184,7 @@ def test_cffmpp_cluster_branch_vs_reference_golden(golden_dir):
     head._cluster_branch(P, tok.view(B * HW, 256).cuda().clone(), centers.cuda(), lg, B, HW)
     e = rel_err(2.0 * lg[:, :124].view(B, HW, 124), g["out"][:, :, :124])
     print(f"CFFM++ cluster layer: rel err {e:.2e}")
-    assert e <= 3e-3, e
+    assert e <= 1e-3, e                                                      # the north_star bar: 1e-3 relative, fp16
 
 
 def test_cffmpp_head_vs_oracle(golden_dir):
@@ -201,7 +201,7 @@ def test_cffmpp_head_vs_oracle(golden_dir):
     got = head.forward([f.cuda() for f in feats], B, T, None, None, centers=centers.cuda())
     e = rel_err(got, ref)
     print(f"CFFM++ head: rel err {e:.2e}")
-    assert e <= 3e-3, e
+    assert e <= 1e-3, e                                                      # the north_star bar: 1e-3 relative, fp16
 
 
 # ------------------------------------------------------------------ full BASELINE size: properties
