@@ -36,6 +36,7 @@ H = W = 480
 T = 4
 CLIPS_PER_GPU = 2
 VARIANT = "b1"
+HEAD_DEPTH = {"b0": 1, "b1": 2, "b2": 2}                            # local_configs/cffm/B*/: decoder_params.depths
 CFM_FLOPS_PER_CLIP_BLOCK = 2 * 2 * 81 * 8 * 49 * 289 * 32            # QK^T + PV, SURVEY.md 8(d): 1.1746 GFLOP
 # fp16 operands each once, per clip per block: Q + target K,V + pooled K,V + O + bias tables
 CFM_BYTES_PER_CLIP_BLOCK = (3969 * 256 * 2) + (3969 * 512 * 2) + (1215 * 512 * 2) + (3600 * 256 * 2) + (8 * 49 * 289 * 4)
@@ -48,6 +49,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shard", default="clips", choices=["clips", "frames"])
+    ap.add_argument("--variant", default="b1", choices=["b0", "b1", "b2"],
+                    help="MiT backbone; b1 is the headline workload (BASELINE configs[1]), b2 = configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -127,11 +130,11 @@ def cpu_reference_time(sd, steps, warmup, clips=1):
     torch.set_num_threads(cores)
     imgs = synth.synth_clip(clips, T, H, W, seed=3)
     for _ in range(warmup):
-        O.segmentor_simple_test(sd, imgs, "mit_" + VARIANT, 2)
+        O.segmentor_simple_test(sd, imgs, "mit_" + VARIANT, HEAD_DEPTH[VARIANT])
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        O.segmentor_simple_test(sd, imgs, "mit_" + VARIANT, 2).numpy()
+        O.segmentor_simple_test(sd, imgs, "mit_" + VARIANT, HEAD_DEPTH[VARIANT]).numpy()
         ts.append(time.perf_counter() - t0)
     mean = sum(ts) / len(ts)
     return clips * T / mean, mean * 1e3, torch.get_num_threads()
@@ -148,7 +151,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": 1, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"MiT-B1 + CFFM (depth 2), {H}x{W}, T={T}, reference's PyTorch path on host CPU cores",
+        "config": {"workload": f"MiT-{VARIANT.upper()} + CFFM (depth {HEAD_DEPTH[VARIANT]}), {H}x{W}, T={T}, reference's PyTorch path on host CPU cores",
                    "note": "the reference is pure Python/PyTorch+mmcv (mmcv absent offline); this is oracle/cffm_oracle.py, the "
                            "CPU port pinned to goldens generated from the unmodified reference"},
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -158,6 +161,9 @@ def run_reference(args, rank):
 
 def main():
     args = parse()
+    global VARIANT, METRIC
+    VARIANT = args.variant
+    METRIC = f"clip-frames/sec (480x480, T=4, MiT-{VARIANT.upper()}+CFFM)"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -409,7 +415,7 @@ def main():
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
-            "config": {"workload": f"MiT-B1 + CFFM head (depth 2), {H}x{W}, T={T}, {B} clips per GPU (BASELINE configs[1])",
+            "config": {"workload": f"MiT-{VARIANT.upper()} + CFFM head (depth {HEAD_DEPTH[VARIANT]}), {H}x{W}, T={T}, {B} clips per GPU" + (" (BASELINE configs[1])" if VARIANT == "b1" else ""),
                        "clips_per_gpu": B, "frames_per_step": B * T * n_gpus, "shard": args.shard if n_gpus > 1 else "none",
                        "l2": "256 MiB flush between timed steps", "timing": "per-step CUDA events, max over ranks"},
             "clocks": clocks,
