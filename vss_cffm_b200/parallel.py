@@ -184,3 +184,31 @@ class FrameShardedRunner:
             ops.resize_nhwc_to_nchw(lg, model.num_classes, logits, n_t, h2, w2, h, w)
             ops.resize_argmax(logits, labels, n_t, model.num_classes, h, w, H, W)
         return labels
+
+
+class GraphedFrameShard:
+    """One frame-sharded pass (kernels + the NCCL all-gather) captured in a CUDA graph and replayed with a single launch per
+    rank.  NCCL collectives are capturable once the communicator exists, hence the eager warm-up runs first; every rank must
+    capture and replay in lock step."""
+
+    def __init__(self, runner, frames, warmup=2):
+        self.runner = runner
+        self.frames = frames                                     # static input buffer: copy new frames into it, then replay()
+        dev = frames.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                runner.run(self.frames)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _abi.n_launches
+        with torch.cuda.graph(self.graph):
+            self.labels = runner.run(self.frames)
+        self.kernels_per_replay = _abi.n_launches - n0
+
+    def replay(self):
+        self.graph.replay()
+        _abi.n_launches += self.kernels_per_replay
+        return self.labels
