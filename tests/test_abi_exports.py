@@ -85,3 +85,19 @@ def test_cpu_tensors_are_rejected_not_silently_computed():
     a = torch.zeros(8, 8, dtype=torch.float16)
     with pytest.raises(_abi.CffmError, match="no CPU fallback"):
         ops.gemm(a, a, out32=torch.zeros(8, 8))
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/cffm_b200.h is the drop-in boundary: it must compile as C (no C++ or torch types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "use.c"
+    src.write_text('#include "cffm_b200.h"\nint main(void) { cffm_patch_or_version(); return 0; }\n'
+                   .replace("cffm_patch_or_version()", "(void)cffm_abi_version"))
+    r = subprocess.run([gcc, "-std=c99", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
