@@ -1,8 +1,8 @@
 """CFFM / CFFM++ decode heads, B200-native.
 
-Plugin surface of the reference (mmseg/models/decode_heads/cffm_head.py:40-157, :303-535 on top of
-decode_head.py:513-708): registered in HEADS as ``CFFMHead_clips_resize1_8`` and
-``CFFMHead_clips_resize1_8_finetune_w_prototype3``; same constructor kwargs, attributes
+Plugin surface of the reference (mmseg/models/decode_heads/cffm_head.py:40-157, :161-300, :303-535 on top of
+decode_head.py:513-708): registered in HEADS as ``CFFMHead_clips_resize1_8``,
+``CFFMHead_clips_resize1_8_finetune_w_prototype3`` and ``CFFMHead_clips_resize1_8_gene_prototype``; same constructor kwargs, attributes
 (``num_classes``, ``align_corners``, ``num_clips`` ...), ``init_weights()``, ``forward_test(...)`` ->
 (B, num_classes, h, w) logits at 1/4 scale, and the SAME state-dict keys / shapes.
 
@@ -12,9 +12,11 @@ The nn.Module tree only HOLDS parameters.  Eval-mode arithmetic is a fixed seque
                  C_i -> 256 projections applied at NATIVE resolution (bilinear upsampling commutes
                  with a 1x1 conv); one kernel then upsamples, sums, ReLUs and emits the 2x2 mean
                  (= resize(_c, 1/2), cffm_head.py:131-133)                     (:102-133)
-  CFFM block   : cffa_norm -> cffa_pool -> qkv GEMMs -> cfm_attention (in-kernel K/V assembling)
-                 -> proj GEMM + residual -> LN -> fc1 GELU -> fc2 + residual
-                 (cffm_transformer.py:709-832); reference frames pass through untouched (:826)
+  CFFM block   : target: norm1 -> pad -> qkv GEMM ; pooled K/V: target-level fc-pool + the three reference
+                 levels (norm1 -> pad -> resize -> fc-pool, produced one block ahead on a side stream:
+                 reference frames are read-only, :826) -> kv GEMM ; cfm_attention (in-kernel K/V
+                 assembling) -> proj GEMM + residual -> LN -> fc1 GELU -> fc2 + residual
+                 (cffm_transformer.py:709-832)
   classifier   : linear_pred2 as two accumulating GEMMs over [c_target | cffm_target] (no concat),
                  then the x2 bilinear resize to NCHW fp32                     (:145-155)
   CFFM++       : prototype cross-attention (swin_transformer_2d.py:208-262, :605-665), linear_pred3

@@ -8,12 +8,15 @@ registered in BACKBONES as ``mit_b0`` .. ``mit_b5``, ``**kwargs`` swallowed (con
 The nn.Module tree below only HOLDS parameters.  The arithmetic is a fixed sequence of C-ABI
 calls (``ops``) on fp16 token-major ("NHWC") activations with an fp32 residual stream:
 
-  patch embed  : im2col -> tcgen05 GEMM(+bias) -> LayerNorm(eps 1e-5)        (:173-200)
-  attention    : LN -> q GEMM ; [sr: im2col -> GEMM -> LN(1e-5)] -> kv GEMM ;
-                 fused softmax(q k^T d^-1/2) v with the <=225 keys in smem ;
-                 proj GEMM + residual (in place)                              (:96-117,:154)
-  Mix-FFN      : LN -> fc1 GEMM -> depthwise 3x3 + GELU -> fc2 GEMM + residual (:48-55,:155)
-  stage output : LN(eps 1e-6) -> fp16 NHWC (also the next stage's im2col input) (:321-349)
+  patch embed  : im2col -> tcgen05 GEMM whose epilogue applies the patch-embed LayerNorm (eps 1e-5) AND the first
+                 block's norm1 (C <= 128), or split-K GEMM + one two-LayerNorm pass over the partial sums  (:173-200)
+  attention    : q GEMM on the main stream ; [sr: im2col -> split-K GEMM -> LN(1e-5)] -> kv GEMM on a side stream ;
+                 tcgen05 attention kernel (TMA Q/K/V, QK^T and PV on tensor cores, S in TMEM; <= 256 keys, else the
+                 mma.sync kernel) ; proj GEMM + residual (in place) + norm2 in its epilogue     (:96-117,:154)
+  Mix-FFN      : fc1 GEMM (TMA-store epilogue) -> depthwise 3x3 + GELU -> fc2 GEMM + residual + the next norm1 /
+                 the stage norm in its epilogue (separate LayerNorm kernels when C > 128)        (:48-55,:155)
+  stage output : fp16 NHWC (also the next stage's im2col input), handed to the decode head's projection at once
+                 through ``stage_hook``                                                           (:321-349)
 """
 import math
 from functools import partial
