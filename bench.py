@@ -415,8 +415,8 @@ def main():
         alg_flops = CFM_FLOPS_PER_CLIP_BLOCK * B
         cgbs = alg_bytes / (cfm_avg_ms * 1e-3) / 1e9
         ctfs = alg_flops / (cfm_avg_ms * 1e-3) / 1e12
-        roofline_cfm = {"kernel": "cfm_attention_kernel", "bound": "hbm", "achieved": round(cgbs, 2), "peak": pk["hbm"],
-                        "unit": "GB/s", "frac": round(cgbs / pk["hbm"], 5), "traffic": ncu_traffic("cfm_attention_kernel"),
+        roofline_cfm = {"kernel": "cfm_attention_tc_kernel", "bound": "hbm", "achieved": round(cgbs, 2), "peak": pk["hbm"],
+                        "unit": "GB/s", "frac": round(cgbs / pk["hbm"], 5), "traffic": ncu_traffic("cfm_attention_tc_kernel"),
                         "tensor_tflops": round(ctfs, 3), "tensor_frac_of_sustained": round(ctfs / pk["tf_sust"], 5),
                         "launch_ms": round(cfm_avg_ms, 5), "launches_timed": len(cfm_ms),
                         "share_of_kernel_time": round(sum(cfm_ms) / eager_ms, 4),

@@ -152,14 +152,17 @@ int cffm_head_fuse(const void* p1, const void* p2, const void* p3, const void* p
 
 /* CFFA step 1: LayerNorm (norm1) of all T frames of x fp32 [T,B,H,W,C] (frame-major; the target
  * frames are the last B) -> xn fp16 (same shape)
- * and the zero-padded target map xt_pad fp16 [B,Hp,Wp,C] (interior rows only are written; the
- * caller zeroes the pad rows once).  cffm_transformer.py:713-734. */
+ * and the target map in the layout the CFM attention reads: xt_pad fp16 [B,Hp+6,Wp+6,C], the
+ * zero-padded LN map (pad AFTER norm) with a 3-wide CYCLIC apron: position (Y,X) holds the padded
+ * map at ((Y-3) mod Hp, (X-3) mod Wp), which materialises the torch.roll wrap-around of the
+ * neighbour windows.  Every position (pad zeros included) is written on every call.
+ * cffm_transformer.py:713-734, :389-400. */
 int cffm_cffa_norm(const float* x, const float* gamma, const float* beta, float eps, void* xn,
                    void* xt_pad, int B, int T, int H, int W, int Hp, int Wp, int C, void* stream);
 
 /* Same kernel on an arbitrary list of frames (frame-sharded multi-GPU path): x fp32 [n_frames,H,W,C];
- * frames >= first_target are target frames and are also written, zero-padded, to xt_pad
- * [n_frames-first_target,Hp,Wp,C] (xt_pad may be NULL when first_target == n_frames). */
+ * frames >= first_target are target frames and are also written, in the apron layout above, to xt_pad
+ * [n_frames-first_target,Hp+6,Wp+6,C] (xt_pad may be NULL when first_target == n_frames). */
 int cffm_cffa_norm_frames(const float* x, const float* gamma, const float* beta, float eps, void* xn,
                           void* xt_pad, int n_frames, int first_target, int H, int W, int Hp, int Wp,
                           int C, void* stream);
@@ -184,19 +187,32 @@ int cffm_cffa_pool_part(const void* xn, int B, int part, int H, int W, int C, co
 int cffm_cffa_pool_level(const void* xn, int n_frames, int level, int H, int W, int C,
                          const float* pool_w, const float* pool_b, void* pooled, void* stream);
 
-/* Cross-frame feature mining attention with in-kernel K/V assembling (no roll / partition /
- * unfold / cat is materialised).  qkv_t fp16 [B, Hp*Wp, 3C] = qkv(xt_pad); kv_pooled fp16
- * [B, P, 2C] = K,V thirds of qkv(pooled); bias fp32 [heads, 64, 320] = window-independent
- * additive term (relative-position tables gathered on the host, rows >= 49 / cols >= 289
- * ignored).  out fp16 [B, H*W, C]: window_reverse + crop already applied.
+/* Cross-frame feature mining attention (TMA-assembled K/V, tcgen05 QK^T / PV; no roll / partition /
+ * unfold / cat is materialised).
+ *   qkv_a     fp16 [B, Hp+6, Wp+6, 3C] = qkv(xt_pad) in the apron layout of cffm_cffa_norm
+ *   kv_pooled fp16 [B, 15 nW, 2C]      = K,V thirds of qkv(pooled); level maps target 9x9-like | ref0 |
+ *                                        ref1 | ref2 at token offsets {0, 1, 2, 6} nW
+ *   bias_tab  fp16 [heads, 49, pitch]  = window-independent additive logit term DIVIDED by `scale`, in
+ *                                        the kernel's key order (cffm_cfm_layout): 13x13 halo of the
+ *                                        window row-major (own window + ring; a ring key the reference
+ *                                        lists twice carries logaddexp of its two entries), then the
+ *                                        5x5 / 7x7 / 5x5 / 3x3 pooled windows; -inf on unused columns
+ *   out       fp16 [B, H*W, C]: window_reverse + crop already applied.
  * C = 256, heads = 8, window 7, expand 3 (the head's hard-coded setting, cffm_head.py:74-95).
  * cffm_transformer.py:364-601 and :809-821. */
-int cffm_cfm_attention(const void* qkv_t, const void* kv_pooled, const float* bias, void* out, int B,
+int cffm_cfm_attention(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void* out, int B,
                        int H, int W, int C, int heads, float scale, void* stream);
 
-/* Debug/test entry: the (level, y, x) source of every key slot exactly as the attention kernel
- * computes it; out int32 [nW, 289, 3], y = x = -1 for zero-filled slots. */
-int cffm_cfm_key_sources(int Hp, int Wp, int32_t* out, void* stream);
+/* Test entry: the same kernel, additionally writing the assembled K and V tiles of every work item
+ * (head pair hp, clip b, window w) to dump fp16 [4, B*nW, 2, NPAD, 64] (K then V; row order =
+ * cffm_cfm_layout) so that the TMA assembling can be compared bit for bit with the reference's
+ * roll / window_partition / valid_ind_rolled / nn.Unfold / cat pipeline (cffm_transformer.py:378-522). */
+int cffm_cfm_attention_dump(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void* out,
+                            void* dump, int B, int H, int W, int C, int heads, float scale, void* stream);
+
+/* Key-row layout of the CFM kernel (host only, no GPU work): out8 = {row of the halo block (0), of the
+ * pooled target block, of reference 0, 1, 2, number of key rows NPAD, bias_tab row pitch, apron width}. */
+int cffm_cfm_layout(int32_t* out8);
 
 /* Bilinear (align_corners=False) resize of NHWC logits to fp32 NCHW.
  * in: fp16 (in_is_f32=0) or fp32 [B,h,w,ldc] using the first ncls channels.

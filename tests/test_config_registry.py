@@ -111,12 +111,27 @@ def test_bias_table_assembly_matches_oracle():
             "a.relative_position_bias_table_to_windows.0": (8, 121), "a.relative_position_bias_table_to_windows_clips.0": (8, 169),
             "a.relative_position_bias_table_to_windows_clips.1": (8, 121), "a.relative_position_bias_table_to_windows_clips.2": (8, 81)}
     sd = synth.synth_state_dict(spec, 2)
-    got = tb.assemble_bias(sd["a.relative_position_bias_table"], sd["a.relative_position_bias_table_to_neighbors"],
-                           sd["a.relative_position_bias_table_to_windows.0"],
-                           [sd[f"a.relative_position_bias_table_to_windows_clips.{k}"] for k in range(3)])
-    assert got.shape == (8, 64, 320)
-    assert torch.equal(got[:, :49, :289], O.cfm_bias_table(sd, "a"))
-    assert got[:, 49:].abs().max() == 0 and got[:, :, 289:].abs().max() == 0
+    from vss_cffm_b200 import ops
+    lay = ops.cfm_layout()                                     # host-only query of the kernel's key-row layout
+    scale = 32 ** -0.5
+    got = tb.assemble_bias_tc(sd["a.relative_position_bias_table"], sd["a.relative_position_bias_table_to_neighbors"],
+                              sd["a.relative_position_bias_table_to_windows.0"],
+                              [sd[f"a.relative_position_bias_table_to_windows_clips.{k}"] for k in range(3)], scale, lay)
+    assert got.shape == (8, 49, lay["pitch"]) and got.dtype == torch.float16
+    ref = O.cfm_bias_table(sd, "a").double()                   # (8, 49, 289) in the reference's key order
+    # fold the reference columns that name the same key (the 12 ring keys listed twice): exp-sum, exactly what the
+    # softmax does with two equal logits + different biases
+    rows = [(n // 7 + 3) * 13 + n % 7 + 3 for n in range(49)] + [(dy + 3) * 13 + dx + 3 for dy, dx in O.ring_offsets()]
+    for blk, cnt in zip(lay["rows"][1:], (25, 49, 25, 9)):
+        rows += [blk + m for m in range(cnt)]
+    want = torch.full((8, 49, lay["npad"]), float("-inf"), dtype=torch.float64)
+    for n, r in enumerate(rows):
+        want[:, :, r] = torch.logaddexp(want[:, :, r], ref[:, :, n])
+    assert len(set(rows)) == 277
+    g = got[:, :, :lay["npad"]].double() * scale
+    used = torch.isfinite(want)
+    assert torch.equal(torch.isfinite(g), used)                # unused key rows carry -inf
+    assert (g[used] - want[used]).abs().max() <= 1e-3 * want[used].abs().max()      # fp16 table
 
 
 def test_modules_refuse_training_and_cpu_execution():

@@ -86,9 +86,9 @@ def _run_cffm_blocks(head, x):
     nW = (Hp // 7) * (Wp // 7)
     dev, h, f = "cuda", torch.float16, torch.float32
     xn = torch.empty(T * B * H * W, C, dtype=h, device=dev)
-    xt_pad = torch.zeros(B * Hp * Wp, C, dtype=h, device=dev)
+    xt_pad = torch.empty(ops.apron_rows(B, H, W), C, dtype=h, device=dev)
     pooled = torch.empty(B * 15 * nW, C, dtype=h, device=dev)
-    qkv_t = torch.empty(B * Hp * Wp, 3 * C, dtype=h, device=dev)
+    qkv_t = torch.empty(ops.apron_rows(B, H, W), 3 * C, dtype=h, device=dev)
     kvp = torch.empty(B * 15 * nW, 2 * C, dtype=h, device=dev)
     ao = torch.empty(B * H * W, C, dtype=h, device=dev)
     xn2 = torch.empty(B * H * W, C, dtype=h, device=dev)

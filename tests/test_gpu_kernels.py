@@ -16,6 +16,7 @@ from vss_cffm_b200 import synth
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
 REL16, REL32 = 1e-3, 1e-4
+CFM_TOL = 1e-3
 
 
 @pytest.fixture(scope="module")
@@ -233,6 +234,13 @@ def test_head_fuse_vs_oracle(ops, t_perm):
 
 
 # ------------------------------------------------------------------------------------------- CFFA
+def _apron(x, Hp, Wp, e=3):
+    """(B,Hp,Wp,C) -> (B,Hp+2e,Wp+2e,C): position (Y,X) holds x[(Y-e) mod Hp, (X-e) mod Wp]."""
+    yi = (torch.arange(Hp + 2 * e) - e) % Hp
+    xi = (torch.arange(Wp + 2 * e) - e) % Wp
+    return x[:, yi][:, :, xi]
+
+
 def _block_sd(seed):
     spec = {"norm1.weight": (256,), "norm1.bias": (256,), "pool_layers.0.weight": (1, 49), "pool_layers.0.bias": (1,),
             "pool_layers_clips.0.weight": (1, 49), "pool_layers_clips.0.bias": (1,),
@@ -252,11 +260,15 @@ def test_cffa_norm_and_pool_vs_oracle(ops, B, H, W):
     xn_pad = F.pad(xn_ref, (0, 0, 0, Wp - W, 0, Hp - H))
     xfm = x.transpose(0, 1).contiguous().cuda()                                   # frame-major for the kernels
     xn = torch.empty(T * B * H * W, C, dtype=torch.float16, device="cuda")
-    xt_pad = torch.zeros(B * Hp * Wp, C, dtype=torch.float16, device="cuda")
+    xt_pad = torch.full((B * (Hp + 6) * (Wp + 6), C), float("nan"), dtype=torch.float16, device="cuda")   # every row must be written
     ops.cffa_norm(xfm, sd["blk.norm1.weight"].cuda(), sd["blk.norm1.bias"].cuda(), 1e-5, xn, xt_pad, B, T, H, W, Hp, Wp, C)
     check(xn.view(T, B, H, W, C), xn_ref.transpose(0, 1), REL16, "norm1")
-    check(xt_pad.view(B, Hp, Wp, C), xn_pad[:, -1], REL16, "padded target")
-    assert xt_pad.view(B, Hp, Wp, C)[:, H:].abs().sum().item() == 0 and xt_pad.view(B, Hp, Wp, C)[:, :, W:].abs().sum().item() == 0
+    # target map in the CFM kernel's layout: zero pad AFTER the norm, then a 3-wide cyclic apron (= torch.roll wrap-around)
+    apron = _apron(xn_pad[:, -1], Hp, Wp)
+    got = xt_pad.view(B, Hp + 6, Wp + 6, C)
+    check(got, apron, REL16, "padded target + apron")
+    assert got[:, 3 + H:3 + Hp, 3:3 + Wp].abs().sum().item() == 0 and got[:, 3:3 + Hp, 3 + W:3 + Wp].abs().sum().item() == 0
+    assert torch.equal(got[:, :3], got[:, Hp:Hp + 3]) and torch.equal(got[:, :, Wp + 3:], got[:, :, 3:6])   # wrap copies are exact
     # pooling on the kernel's own fp16 LN output (isolates the pool kernel)
     xn16 = xn.view(T, B, H, W, C).float().cpu().transpose(0, 1)
     pooled_ref = O.cffa_assemble(sd, "blk", F.pad(xn16, (0, 0, 0, Wp - W, 0, Hp - H)))
@@ -283,18 +295,89 @@ def test_cffa_norm_and_pool_vs_oracle(ops, B, H, W):
 
 
 # ------------------------------------------------------------------------------------ CFM attention
-@pytest.mark.parametrize("Hp,Wp", [(21, 28), (63, 63), (14, 14)])
-def test_cfm_key_sources_bit_exact(ops, golden_dir, Hp, Wp):
-    """In-kernel K/V source coordinates == oracle table == what the reference's roll / partition /
-    unfold / cat builds (golden key codes, cffm_transformer.py:378-522)."""
+def _kernel_row_of_reference_key(lay):
+    """Row of the CFM kernel's key tile that holds reference key n (column n of the reference's logits, 0..288):
+    own window and ring -> the 13 x 13 halo (a ring key listed twice maps to one row), pooled windows -> their blocks."""
+    rows = []
+    for n in range(49):
+        rows.append((n // 7 + 3) * 13 + n % 7 + 3)
+    for dy, dx in O.ring_offsets():
+        rows.append((dy + 3) * 13 + dx + 3)
+    for blk, cnt in zip(lay["rows"][1:], (25, 49, 25, 9)):
+        rows += [blk + m for m in range(cnt)]
+    assert len(rows) == 289 and len(set(rows)) == 277
+    return torch.tensor(rows)
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 21, 28), (2, 60, 60), (1, 14, 14), (1, 7, 12)])
+def test_cfm_key_assembling_bit_exact(ops, golden_dir, B, H, W):
+    """The K and V tiles the CFM kernel's TMA boxes assemble == the key sequence the reference's roll /
+    window_partition / valid_ind_rolled / nn.Unfold / cat builds (cffm_transformer.py:378-522), bit for bit:
+    every source position carries its own (clip, level, y, x) code, the tiles are dumped and compared with the oracle's
+    source table (itself pinned to the reference-generated golden key codes, 63x63 included)."""
     import os
-    got = ops.cfm_key_sources(Hp, Wp, "cuda").cpu().long()
-    lev, ys, xs = O.key_source_table(Hp, Wp)
-    assert torch.equal(got[..., 1], ys) and torch.equal(got[..., 2], xs)
-    assert torch.equal(torch.where(ys < 0, lev, got[..., 0]), lev)
+    C = 256
+    Hp, Wp = (H + 6) // 7 * 7, (W + 6) // 7 * 7
+    nWh, nWw = Hp // 7, Wp // 7
+    nW = nWh * nWw
+    lay = ops.cfm_layout()
+    ch = torch.arange(C)
+
+    def coded(level, b, ys, xs, is_v):
+        """[len(ys), C] codes: channel c carries (y, x, 10 level + is_v, 16 b + c // 32) for c % 4 = 0..3; level 0 uses
+        1-based y so that a real row is never all zero."""
+        out = torch.empty(len(ys), C)
+        out[:, ch % 4 == 0] = (ys[:, None] + 1).float().expand(-1, C // 4)
+        out[:, ch % 4 == 1] = (xs[:, None] + 1).float().expand(-1, C // 4)
+        out[:, ch % 4 == 2] = float(10 * level + is_v + 1)
+        out[:, ch % 4 == 3] = (16 * b + ch[ch % 4 == 3] // 32 + 1).float()[None].expand(len(ys), -1)
+        return out
+
+    Ha, Wa = Hp + 6, Wp + 6
+    qkv_a = torch.zeros(B, Ha, Wa, 3 * C)
+    yy, xx = torch.meshgrid(torch.arange(Ha), torch.arange(Wa), indexing="ij")
+    ys0, xs0 = ((yy - 3) % Hp).reshape(-1), ((xx - 3) % Wp).reshape(-1)
+    sizes = [(nWh, nWw), (nWh, nWw), (2 * nWh, 2 * nWw), (3 * nWh, 3 * nWw)]
+    kvp = torch.zeros(B, 15 * nW, 2 * C)
+    for b in range(B):
+        qkv_a[b, :, :, C:2 * C] = coded(0, b, ys0, xs0, 0).view(Ha, Wa, C)
+        qkv_a[b, :, :, 2 * C:] = coded(0, b, ys0, xs0, 1).view(Ha, Wa, C)
+        off = 0
+        for l, (gh, gw) in enumerate(sizes):
+            gy, gx = torch.meshgrid(torch.arange(gh), torch.arange(gw), indexing="ij")
+            kvp[b, off:off + gh * gw, :C] = coded(l + 1, b, gy.reshape(-1), gx.reshape(-1), 0)
+            kvp[b, off:off + gh * gw, C:] = coded(l + 1, b, gy.reshape(-1), gx.reshape(-1), 1)
+            off += gh * gw
+    assert qkv_a.max() < 2048 and kvp.max() < 2048                                # exact in fp16
+    bias = torch.zeros(8, 49, lay["pitch"], dtype=torch.float16, device="cuda")
+    out = torch.empty(B * H * W, C, dtype=torch.float16, device="cuda")
+    dump = torch.full((4, B * nW, 2, lay["npad"], 64), float("nan"), dtype=torch.float16, device="cuda")
+    ops.cfm_attention(qkv_a.view(-1, 3 * C).cuda().half(), kvp.view(-1, 2 * C).cuda().half(), bias, out, B, H, W, C, 8,
+                      32 ** -0.5, dump=dump)
+    got = dump.float().cpu()                                                       # [hp, item, K|V, row, 64]
+    assert not torch.isnan(got).any()
+    lev, ys, xs = O.key_source_table(Hp, Wp)                                       # (nW, 289), reference key order
+    rows = _kernel_row_of_reference_key(lay)
+    used = torch.zeros(lay["npad"], dtype=torch.bool)
+    used[rows] = True
+    c64 = torch.arange(64)
+    for hp in range(4):
+        for b in range(B):
+            for is_v in (0, 1):
+                tile = got[hp, b * nW:(b + 1) * nW, is_v]                          # (nW, npad, 64)
+                ref = torch.zeros(nW, 289, 64)
+                ok = (ys >= 0)[..., None].float()
+                ref[..., c64 % 4 == 0] = ((ys + 1)[..., None] * ok).expand(-1, -1, 16)
+                ref[..., c64 % 4 == 1] = ((xs + 1)[..., None] * ok).expand(-1, -1, 16)
+                ref[..., c64 % 4 == 2] = (10 * lev + is_v + 1)[..., None].float().expand(-1, -1, 16) * ok
+                ref[..., c64 % 4 == 3] = (16 * b + (hp * 64 + c64[c64 % 4 == 3]) // 32 + 1).float()[None, None] * ok
+                assert torch.equal(tile[:, rows], ref), (hp, b, is_v)              # every reference key, duplicates included
+                assert tile[:, ~used].abs().sum() == 0                             # rows no reference key maps to stay zero
     t = np.load(os.path.join(golden_dir, "index_tables.npz"))
-    if f"key_code_{Hp}x{Wp}" in t:
-        code = torch.where(got[..., 1] < 0, torch.zeros_like(ys), got[..., 0] * 10000 + got[..., 1] * 100 + got[..., 2] + 1)
+    if f"key_code_{Hp}x{Wp}" in t:                                                 # the reference's own key codes
+        k0 = got[0, :nW, 0][:, rows]                                               # clip 0, head pair 0, K tile
+        y1, x1, lv = k0[..., 0].long(), k0[..., 1].long(), (k0[..., 2].long() - 1) // 10
+        code = torch.where(y1 == 0, torch.zeros_like(y1), lv * 10000 + (y1 - 1) * 100 + (x1 - 1) + 1)
         assert np.array_equal(code.to(torch.int32).numpy(), t[f"key_code_{Hp}x{Wp}"])
 
 
@@ -307,7 +390,7 @@ def _attn_sd(golden_dir, seed):
             for k, s in spec.items() if k.startswith(pre) and not synth.is_derived_buffer(k)}
 
 
-@pytest.mark.parametrize("B,H,W", [(1, 21, 28), (2, 20, 25), (1, 60, 60)])
+@pytest.mark.parametrize("B,H,W", [(1, 21, 28), (2, 20, 25), (1, 60, 60), (2, 60, 108), (1, 7, 7)])
 def test_cfm_attention_vs_oracle(ops, golden_dir, B, H, W):
     """qkv GEMMs + CFM attention kernel == oracle cfm_attention before proj (cffm_transformer.py:364-601)."""
     C, heads = 256, 8
@@ -324,20 +407,23 @@ def test_cfm_attention_vs_oracle(ops, golden_dir, B, H, W):
     ref = O.cfm_attention(sd, "attn", xt, pooled)                                  # (B*nW, 49, C)
     ref = ref.view(B, nWh, nWw, 7, 7, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, C)[:, :H, :W]
     qw, qb = sd["attn.qkv.weight"].cuda().half(), sd["attn.qkv.bias"].cuda()
-    qkv_t = torch.empty(B * Hp * Wp, 3 * C, dtype=torch.float16, device="cuda")
-    ops.gemm(xt.view(-1, C).cuda().half(), qw, bias=qb, out16=qkv_t)
+    xa = _apron(xt, Hp, Wp).reshape(-1, C).cuda().half()                           # what cffa_norm hands to the QKV GEMM
+    qkv_a = torch.empty(xa.shape[0], 3 * C, dtype=torch.float16, device="cuda")
+    ops.gemm(xa, qw, bias=qb, out16=qkv_a)
     pl = torch.cat([p.reshape(B, -1, C) for p in pooled], 1).reshape(-1, C).cuda().half()
     kvp = torch.empty(B * 15 * nW, 2 * C, dtype=torch.float16, device="cuda")
     ops.gemm(pl, qw[C:], bias=qb[C:], out16=kvp)
-    bias = tb.assemble_bias(sd["attn.relative_position_bias_table"].cuda(),
-                            sd["attn.relative_position_bias_table_to_neighbors"].cuda(),
-                            sd["attn.relative_position_bias_table_to_windows.0"].cuda(),
-                            [sd[f"attn.relative_position_bias_table_to_windows_clips.{k}"].cuda() for k in range(3)])
-    check(bias[:, :49, :289], O.cfm_bias_table(sd, "attn"), 0.0, "bias table (bit-exact gather)")
-    out = torch.empty(B * H * W, C, dtype=torch.float16, device="cuda")
-    ops.cfm_attention(qkv_t, kvp, bias, out, B, H, W, C, heads, (C // heads) ** -0.5)
-    # q, k, v are rounded to fp16 by the GEMM, P by the kernel: 3e-3 of the output scale
-    check(out.view(B, H, W, C), ref, 3e-3, "cfm attention")
+    scale = (C // heads) ** -0.5
+    bias = tb.assemble_bias_tc(sd["attn.relative_position_bias_table"].cuda(),
+                               sd["attn.relative_position_bias_table_to_neighbors"].cuda(),
+                               sd["attn.relative_position_bias_table_to_windows.0"].cuda(),
+                               [sd[f"attn.relative_position_bias_table_to_windows_clips.{k}"].cuda() for k in range(3)],
+                               scale, ops.cfm_layout())
+    out = torch.full((B * H * W, C), float("nan"), dtype=torch.float16, device="cuda")
+    ops.cfm_attention(qkv_a, kvp, bias, out, B, H, W, C, heads, scale)
+    # q, k, v are rounded to fp16 by the GEMM, P by the kernel
+    e = check(out.view(B, H, W, C), ref, CFM_TOL, "cfm attention")
+    print(f"cfm attention {B}x{H}x{W}: rel err {e:.2e}")
 
 
 # ------------------------------------------------------------------------------------------- tails

@@ -44,10 +44,13 @@ elif which == "mha":
     fn = lambda: ops.mha(q, kv[:, :64], kv[:, 64:], out, Nf, Nq, Nkv, heads, d, d ** -0.5)
 elif which == "cfm":
     B, H, W, E = 2, 60, 60, 256
-    Hp = Wp = 63
     nW = 81
-    qkv_t, kvp = rn(B * Hp * Wp, 3 * E).half(), rn(B * 15 * nW, 2 * E).half()
-    bias, out = rn(8, 64, 320) * 0.1, torch.empty(B * H * W, E, device="cuda", dtype=torch.half)
+    from vss_cffm_b200 import cffm_tables as tb
+    lay = ops.cfm_layout()
+    qkv_t, kvp = rn(ops.apron_rows(B, H, W), 3 * E).half(), rn(B * 15 * nW, 2 * E).half()
+    bias = tb.assemble_bias_tc(rn(169, 8) * 0.1, rn(1, 8, 49, 132) * 0.1, rn(8, 121) * 0.1, [rn(8, 169) * 0.1, rn(8, 121) * 0.1, rn(8, 81) * 0.1],
+                               32 ** -0.5, lay)
+    out = torch.empty(B * H * W, E, device="cuda", dtype=torch.half)
     fn = lambda: ops.cfm_attention(qkv_t, kvp, bias, out, B, H, W, E, 8, 32 ** -0.5)
 elif which == "ln":
     M, C = 115200, 64

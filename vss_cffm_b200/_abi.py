@@ -52,7 +52,8 @@ SIGNATURES = {
     "cffm_kmeans_update": ([vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp], i32),
     "cffm_transpose_f16": ([vp, i32, i32, vp, i32, vp], i32),
     "cffm_cfm_attention": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),
-    "cffm_cfm_key_sources": ([i32, i32, vp, vp], i32),
+    "cffm_cfm_attention_dump": ([vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),
+    "cffm_cfm_layout": ([vp], i32),
     "cffm_resize_nhwc_to_nchw": ([vp, i32, i64, vp, i32, i32, i32, i32, i32, i32, vp], i32),
     "cffm_resize_argmax": ([vp, vp, i32, i32, i32, i32, i32, i32, vp], i32),
     "cffm_upsample2_argmax": ([vp, i64, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),

@@ -297,9 +297,10 @@ class CFFMHead_clips_resize1_8(BaseDecodeHead_clips_flow):
                 pool_b=f(torch.cat([p.bias.detach().reshape(-1) for p in pools])),
                 qkv_w=h(a.qkv.weight), qkv_b=f(a.qkv.bias),
                 proj_w=h(a.proj.weight), proj_b=f(a.proj.bias),
-                bias=tb.assemble_bias(f(a.relative_position_bias_table), f(a.relative_position_bias_table_to_neighbors),
-                                      f(a.relative_position_bias_table_to_windows[0]),
-                                      [f(t) for t in a.relative_position_bias_table_to_windows_clips], HEADS_N),
+                bias=tb.assemble_bias_tc(f(a.relative_position_bias_table), f(a.relative_position_bias_table_to_neighbors),
+                                         f(a.relative_position_bias_table_to_windows[0]),
+                                         [f(t) for t in a.relative_position_bias_table_to_windows_clips],
+                                         (E // HEADS_N) ** -0.5, ops.cfm_layout(), HEADS_N),
                 f1w=h(blk.mlp.fc1.weight), f1b=f(blk.mlp.fc1.bias), f2w=h(blk.mlp.fc2.weight), f2b=f(blk.mlp.fc2.bias)))
         if self.WITH_PROTOTYPES:
             blk = self.decoder_swin.blocks[0]
@@ -444,8 +445,9 @@ class CFFMHead_clips_resize1_8(BaseDecodeHead_clips_flow):
         Pp = 15 * nW
         nref = (T - 1) * B                                       # frame-major: reference frames first, targets last
         xn_t = ws.get("xn_t", (B * HW, E), _H)
-        xt_pad = ws.get("xt_pad", (B * Hp * Wp, E), _H, zero=True)     # pad rows stay zero (pad AFTER norm, :716-724)
-        qkv_t = ws.get("qkv_t", (B * Hp * Wp, 3 * E), _H)
+        na = ops.apron_rows(B, h2, w2)                           # target map with its cyclic apron [B, Hp+6, Wp+6]
+        xt_pad = ws.get("xt_pad", (na, E), _H)                   # every row (pad zeros included) is rewritten per call
+        qkv_t = ws.get("qkv_t", (na, 3 * E), _H)
         ao = ws.get("ao", (B * HW, E), _H)
         xn2 = ws.get("xn2", (B * HW, E), _H)
         hid = ws.get("hid", (B * HW, 4 * E), _H)

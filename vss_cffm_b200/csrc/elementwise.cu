@@ -580,16 +580,41 @@ head_fuse_pyramid_kernel(const __half* __restrict__ p1, const __half* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// CFFA norm: LN over C = 256 of every frame; one warp per token, 8 channels per lane.
+// CFFA norm: LN over C = 256 of every frame; one warp per OUTPUT row, 8 channels per lane.
+// Reference frames: one row of xn per token.  Target frames: one row per position of the cyclic-apron map
+// xt_apron [n_t, Hp+6, Wp+6, C] that the CFM attention reads its 13 x 13 key halos from: position (Y, X) holds the
+// zero-padded LN map (pad AFTER norm, cffm_transformer.py:716-724) at ((Y-3) mod Hp, (X-3) mod Wp), i.e. the
+// torch.roll wrap-around of :389-400 is materialised once here.  Pad positions are written (as zeros) on every call,
+// so the buffer carries no state from an earlier geometry.  The un-wrapped copy of a real token also goes to xn.
 __global__ void __launch_bounds__(256)
 cffa_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 float eps, __half* __restrict__ xn, __half* __restrict__ xt_pad, int n_frames, int first_target, int H,
+                 float eps, __half* __restrict__ xn, __half* __restrict__ xt_apron, int n_frames, int first_target, int H,
                  int W, int Hp, int Wp) {
   pdl_sync();
-  constexpr int C = 256;
-  const int64_t tok = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  constexpr int C = 256, RING = 3;
+  const int64_t row = blockIdx.x * 8ll + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (tok >= static_cast<int64_t>(n_frames) * H * W) return;
+  const int64_t ref_rows = static_cast<int64_t>(first_target) * H * W;
+  const int Ha = Hp + 2 * RING, Wa = Wp + 2 * RING;
+  int64_t tok;                                                  // source token, or -1: zero row
+  __half* dst_apron = nullptr;
+  bool to_xn = true;
+  if (row < ref_rows) {
+    tok = row;
+  } else {
+    const int64_t pos = row - ref_rows;
+    if (pos >= static_cast<int64_t>(n_frames - first_target) * Ha * Wa) return;
+    const int X = static_cast<int>(pos % Wa), Y = static_cast<int>((pos / Wa) % Ha);
+    const int bi = static_cast<int>(pos / (static_cast<int64_t>(Wa) * Ha));
+    const int yy = (Y - RING + Hp) % Hp, xx = (X - RING + Wp) % Wp;
+    dst_apron = xt_apron + pos * C + lane * 8;
+    to_xn = (Y - RING == yy) && (X - RING == xx);
+    tok = (yy < H && xx < W) ? (static_cast<int64_t>(first_target + bi) * H + yy) * W + xx : -1;
+    if (tok < 0) {
+      *reinterpret_cast<half8*>(dst_apron) = zero_half8();
+      return;
+    }
+  }
   const float* px = x + tok * C + lane * 8;
   const float4 a = *reinterpret_cast<const float4*>(px), b = *reinterpret_cast<const float4*>(px + 4);
   float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -608,12 +633,8 @@ cffa_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 #pragma unroll
   for (int e = 0; e < 8; ++e) v[e] = v[e] * rstd * gg[e] + bb[e];
   const half8 o = pack8(v);
-  *reinterpret_cast<half8*>(xn + tok * C + lane * 8) = o;
-  const int xx = static_cast<int>(tok % W), yy = static_cast<int>((tok / W) % H);
-  const int frame = static_cast<int>(tok / (static_cast<int64_t>(W) * H));   // frame-major: frame = t*B + b
-  const int bi = frame - first_target;                          // frames >= first_target are target frames
-  if (bi >= 0 && xt_pad != nullptr)
-    *reinterpret_cast<half8*>(xt_pad + ((static_cast<int64_t>(bi) * Hp + yy) * Wp + xx) * C + lane * 8) = o;
+  if (to_xn) *reinterpret_cast<half8*>(xn + tok * C + lane * 8) = o;
+  if (dst_apron) *reinterpret_cast<half8*>(dst_apron) = o;
 }
 
 // CFFA pooling: one warp per pooled token. Levels: 0 target 7x7 | 1 ref0 7x7 | 2 ref1 resize+3x3 | 3 ref2 resize+2x2
@@ -1078,8 +1099,9 @@ extern "C" int cffm_cffa_norm(const float* x, const float* gamma, const float* b
   CFFM_REQUIRE(x && gamma && beta && xn && xt_pad, CFFM_E_BADARG, "cffa_norm: null pointer");
   CFFM_REQUIRE(B > 0 && T > 0 && H > 0 && W > 0 && Hp >= H && Wp >= W, CFFM_E_BADARG, "cffa_norm: bad size");
   CFFM_REQUIRE(C == 256, CFFM_E_UNSUPPORTED, "cffa_norm: built for C=256, got %d", C);
-  const int64_t tokens = static_cast<int64_t>(B) * T * H * W;
-  launch_k(cffa_norm_kernel, static_cast<int>((tokens + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
+  CFFM_REQUIRE(Hp % 7 == 0 && Wp % 7 == 0, CFFM_E_BADARG, "cffa_norm: Hp, Wp must be multiples of the window size 7");
+  const int64_t rows = static_cast<int64_t>(B) * (T - 1) * H * W + static_cast<int64_t>(B) * (Hp + 6) * (Wp + 6);
+  launch_k(cffa_norm_kernel, static_cast<int>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
       x, gamma, beta, eps, static_cast<__half*>(xn), static_cast<__half*>(xt_pad), B * T, (T - 1) * B, H, W, Hp, Wp);
   return launch_status("cffa_norm_kernel");
 }
@@ -1092,8 +1114,9 @@ extern "C" int cffm_cffa_norm_frames(const float* x, const float* gamma, const f
                CFFM_E_BADARG, "cffa_norm_frames: bad size");
   CFFM_REQUIRE(first_target == n_frames || xt_pad, CFFM_E_BADARG, "cffa_norm_frames: xt_pad required when targets exist");
   CFFM_REQUIRE(C == 256, CFFM_E_UNSUPPORTED, "cffa_norm_frames: built for C=256, got %d", C);
-  const int64_t tokens = static_cast<int64_t>(n_frames) * H * W;
-  launch_k(cffa_norm_kernel, static_cast<int>((tokens + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), x, gamma,
+  CFFM_REQUIRE(Hp % 7 == 0 && Wp % 7 == 0, CFFM_E_BADARG, "cffa_norm_frames: Hp, Wp must be multiples of the window size 7");
+  const int64_t rows = static_cast<int64_t>(first_target) * H * W + static_cast<int64_t>(n_frames - first_target) * (Hp + 6) * (Wp + 6);
+  launch_k(cffa_norm_kernel, static_cast<int>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), x, gamma,
            beta, eps, static_cast<__half*>(xn), static_cast<__half*>(xt_pad), n_frames, first_target, H, W, Hp, Wp);
   return launch_status("cffa_norm_kernel");
 }

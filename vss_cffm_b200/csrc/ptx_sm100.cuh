@@ -67,6 +67,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// 4-D tiled load global -> shared (coordinates innermost first); out-of-range elements of the box are zero-filled,
+// the mbarrier still receives the full box byte count.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1,
+                                            int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+
 // 2-D tiled store shared -> global (bulk async group).  The generic-proxy writes that filled the tile must be
 // ordered before it with fence_proxy_async() by the writing threads; out-of-bounds rows / columns are clipped.
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
@@ -163,6 +174,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+
+// d = a * b + c with fp16 a, b taken from the two halves of packed registers and fp32 c, d: one FHFMA each, the
+// half -> float conversion of a packed operand is free (sm_100 mixed-precision FMA, PTX ISA 8.6).
+__device__ __forceinline__ void fhfma2(uint32_t a_packed, float c_lo, float c_hi, float& d_lo, float& d_hi) {
+  asm("{\n\t.reg .b16 lo, hi, one;\n\t"
+      "mov.b32 {lo, hi}, %2;\n\t"
+      "mov.b16 one, 0x3c00;\n\t"
+      "fma.rn.f32.f16 %0, lo, one, %3;\n\t"
+      "fma.rn.f32.f16 %1, hi, one, %4;\n\t}"
+      : "=f"(d_lo), "=f"(d_hi)
+      : "r"(a_packed), "f"(c_lo), "f"(c_hi));
 }
 
 // ------------------------------------------------------------------ legacy warp MMA (attention kernels)

@@ -186,7 +186,7 @@ def head_fuse(p, sizes, N, C, t_perm, shift, c_full=None, half32=None, half16=No
 def cffa_norm(x, gamma, beta, eps, xn, xt_pad, B, T, H, W, Hp, Wp, C):
     _chk(x, _F, "cffa_norm.x"); _chk(xn, _H, "cffa_norm.xn"); _chk(xt_pad, _H, "cffa_norm.xt_pad")
     assert x.is_contiguous() and xn.is_contiguous() and xt_pad.is_contiguous()
-    assert x.numel() == B * T * H * W * C == xn.numel() and xt_pad.numel() == B * Hp * Wp * C
+    assert x.numel() == B * T * H * W * C == xn.numel() and xt_pad.numel() == B * (Hp + 6) * (Wp + 6) * C
     _abi.call("cffm_cffa_norm", _ptr(x), _ptr(gamma), _ptr(beta), float(eps), _ptr(xn), _ptr(xt_pad), B, T, H, W, Hp,
               Wp, C, _stream())
 
@@ -212,7 +212,7 @@ def cffa_norm_frames(x, gamma, beta, eps, xn, xt_pad, n_frames, first_target, H,
     assert x.is_contiguous() and xn.is_contiguous() and x.numel() == n_frames * H * W * C == xn.numel()
     if xt_pad is not None:
         _chk(xt_pad, _H, "cffa_norm_frames.xt_pad")
-        assert xt_pad.is_contiguous() and xt_pad.numel() == (n_frames - first_target) * Hp * Wp * C
+        assert xt_pad.is_contiguous() and xt_pad.numel() == (n_frames - first_target) * (Hp + 6) * (Wp + 6) * C
     _abi.call("cffm_cffa_norm_frames", _ptr(x), _ptr(gamma), _ptr(beta), float(eps), _ptr(xn), _ptr(xt_pad), n_frames,
               first_target, H, W, Hp, Wp, C, _stream())
 
@@ -223,18 +223,41 @@ def cffa_pool_level(xn, n_frames, level, H, W, C, pool_w, pool_b, pooled):
     _abi.call("cffm_cffa_pool_level", _ptr(xn), n_frames, level, H, W, C, _ptr(pool_w), _ptr(pool_b), _ptr(pooled), _stream())
 
 
-def cfm_attention(qkv_t, kv_pooled, bias, out, B, H, W, C, heads, scale):
-    _chk(qkv_t, _H, "cfm.qkv_t"); _chk(kv_pooled, _H, "cfm.kv_pooled"); _chk(bias, _F, "cfm.bias"); _chk(out, _H, "cfm.out")
-    assert qkv_t.is_contiguous() and kv_pooled.is_contiguous() and bias.is_contiguous() and out.is_contiguous()
-    assert tuple(bias.shape) == (heads, 64, 320)
-    _abi.call("cffm_cfm_attention", _ptr(qkv_t), _ptr(kv_pooled), _ptr(bias), _ptr(out), B, H, W, C, heads,
-              float(scale), _stream())
+_cfm_layout = None
 
 
-def cfm_key_sources(Hp, Wp, device):
-    out = torch.empty((Hp // 7) * (Wp // 7), 289, 3, dtype=torch.int32, device=device)
-    _abi.call("cffm_cfm_key_sources", Hp, Wp, _ptr(out), _stream())
-    return out
+def cfm_layout():
+    """Key-row layout of the CFM kernel: {"rows": [halo, pooled target, ref0, ref1, ref2], "npad", "pitch", "apron"}."""
+    global _cfm_layout
+    if _cfm_layout is None:
+        import ctypes
+        buf = (ctypes.c_int32 * 8)()
+        _abi.check(_abi.load().cffm_cfm_layout(ctypes.cast(buf, ctypes.c_void_p)), "cffm_cfm_layout")
+        _cfm_layout = {"rows": list(buf[0:5]), "npad": buf[5], "pitch": buf[6], "apron": buf[7]}
+    return _cfm_layout
+
+
+def apron_rows(B, H, W):
+    """Rows of the target map in the CFM kernel's cyclic-apron layout [B, Hp+6, Wp+6]."""
+    return B * ((H + 6) // 7 * 7 + 6) * ((W + 6) // 7 * 7 + 6)
+
+
+def cfm_attention(qkv_a, kv_pooled, bias_tab, out, B, H, W, C, heads, scale, dump=None):
+    """qkv_a fp16 [B*(Hp+6)*(Wp+6), 3C] (apron layout), kv_pooled fp16 [B*15*nW, 2C], bias_tab = cffm_tables.assemble_bias_tc."""
+    _chk(qkv_a, _H, "cfm.qkv_a"); _chk(kv_pooled, _H, "cfm.kv_pooled"); _chk(bias_tab, _H, "cfm.bias_tab"); _chk(out, _H, "cfm.out")
+    assert qkv_a.is_contiguous() and kv_pooled.is_contiguous() and bias_tab.is_contiguous() and out.is_contiguous()
+    lay = cfm_layout()
+    assert tuple(bias_tab.shape) == (heads, 49, lay["pitch"]), (tuple(bias_tab.shape), lay)
+    nW = ((H + 6) // 7) * ((W + 6) // 7)
+    assert qkv_a.numel() == apron_rows(B, H, W) * 3 * C and kv_pooled.numel() == B * 15 * nW * 2 * C and out.numel() == B * H * W * C
+    if dump is None:
+        _abi.call("cffm_cfm_attention", _ptr(qkv_a), _ptr(kv_pooled), _ptr(bias_tab), _ptr(out), B, H, W, C, heads,
+                  float(scale), _stream())
+    else:
+        _chk(dump, _H, "cfm.dump")
+        assert dump.is_contiguous() and dump.numel() == 4 * B * nW * 2 * lay["npad"] * 64
+        _abi.call("cffm_cfm_attention_dump", _ptr(qkv_a), _ptr(kv_pooled), _ptr(bias_tab), _ptr(out), _ptr(dump), B, H, W, C,
+                  heads, float(scale), _stream())
 
 
 def resize_nhwc_to_nchw(x, ncls, out, B, h, w, Ho, Wo):

@@ -150,10 +150,10 @@ class FrameShardedRunner:
         xt = x32[n_ref * HW:(n_ref + n_t) * HW]
         ct16 = c16[n_ref * HW:(n_ref + n_t) * HW]
         xn_t = ws.get("xn_t", (n_t * HW, E), _H, device=dev)
-        xt_pad = ws.get("xt_pad", (n_t * Hp * Wp, E), _H, device=dev, zero=True)
+        xt_pad = ws.get("xt_pad", (ops.apron_rows(n_t, h2, w2), E), _H, device=dev)
         pooled_t = ws.get("pooled_t", (n_t * nW, E), _H, device=dev)
         kv_t = ws.get("kv_t", (n_t * nW, 2 * E), _H, device=dev)
-        qkv_t = ws.get("qkv_t", (n_t * Hp * Wp, 3 * E), _H, device=dev)
+        qkv_t = ws.get("qkv_t", (ops.apron_rows(n_t, h2, w2), 3 * E), _H, device=dev)
         kvp = ws.get("kvp", (n_t, 15 * nW, 2 * E), _H, device=dev)
         ao = ws.get("ao", (n_t * HW, E), _H, device=dev)
         xn2 = ws.get("xn2", (n_t * HW, E), _H, device=dev)

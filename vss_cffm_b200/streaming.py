@@ -139,10 +139,10 @@ class VideoStream:
         # ---- target: CFFM blocks with the cached reference K/V (cffm_transformer.py:709-832)
         xt, ct16 = x32, c16
         xn_t = ws.get("xn_t", (B * HW, E), _H, device=dev)
-        xt_pad = ws.get("xt_pad", (B * Hp * Wp, E), _H, device=dev, zero=True)
+        xt_pad = ws.get("xt_pad", (ops.apron_rows(B, h2, w2), E), _H, device=dev)
         pooled_t = ws.get("pooled_t", (B * nW, E), _H, device=dev)
         kv_t = ws.get("kv_t", (B * nW, 2 * E), _H, device=dev)
-        qkv_t = ws.get("qkv_t", (B * Hp * Wp, 3 * E), _H, device=dev)
+        qkv_t = ws.get("qkv_t", (ops.apron_rows(B, h2, w2), 3 * E), _H, device=dev)
         kvp = ws.get("kvp", (B, 15 * nW, 2 * E), _H, device=dev)
         ao = ws.get("ao", (B * HW, E), _H, device=dev)
         xn2 = ws.get("xn2", (B * HW, E), _H, device=dev)
