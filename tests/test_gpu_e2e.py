@@ -293,3 +293,49 @@ def test_cuda_graph_replay_equals_eager(full_model):
         graphed = runner([t.pin_memory() for t in imgs]).clone()
         torch.cuda.synchronize()
         assert torch.equal(eager, graphed)
+
+
+def test_mmseg_call_replays_a_cached_graph():
+    """``model(img=..., return_loss=False)`` -- the reference-facing call -- captures the pass on the second call with the
+    same geometry and replays it afterwards; labels are bit-identical to the eager path, also across geometries and after
+    the weights change."""
+    m = build("b0", seed=41)
+    metas = [synth.img_metas(1, 64, 96)]
+    outs = []
+    for seed in (1, 2, 3, 1):
+        imgs = synth.synth_clip(1, 4, 64, 96, seed=seed)
+        eager = m.predict_labels(imgs, metas[0]).cpu().numpy()
+        got = m(img=[imgs], img_metas=metas, return_loss=False)
+        assert np.array_equal(got[0], eager[0]), seed
+        outs.append(got[0])
+    assert len(m._graphs) == 1 and np.array_equal(outs[0], outs[3])
+    # another geometry: first call eager, second captured, the first geometry's graph stays valid
+    metas2 = [synth.img_metas(1, 96, 64)]
+    for seed in (4, 5, 6):
+        imgs2 = synth.synth_clip(1, 4, 96, 64, seed=seed)
+        eager = m.predict_labels(imgs2, metas2[0]).cpu().numpy()
+        assert np.array_equal(m(img=[imgs2], img_metas=metas2, return_loss=False)[0], eager[0])
+    assert len(m._graphs) == 2
+    imgs = synth.synth_clip(1, 4, 64, 96, seed=2)
+    assert np.array_equal(m(img=[imgs], img_metas=metas, return_loss=False)[0], outs[1])
+    # new weights drop the captured passes
+    synth.fill_module(m, 42)
+    m.load_state_dict(m.state_dict())
+    assert not getattr(m, "_graphs", {})
+    fresh = build("b0", seed=42)
+    assert np.array_equal(m(img=[imgs], img_metas=metas, return_loss=False)[0],
+                          fresh(img=[imgs], img_metas=metas, return_loss=False)[0])
+
+
+@pytest.mark.parametrize("sizes", [[(64, 104), (104, 64), (64, 104)], [(64, 96), (64, 104), (64, 96)]])
+def test_mixed_geometries_on_one_model_equal_fresh_models(sizes):
+    """Videos of different resolution through ONE model instance (workspace buffers re-used across geometries with the
+    same padded size, e.g. 8x13 and 13x8 tokens -> 14x14 windows): every result equals a fresh model's.  The pad
+    positions of the target map are rewritten on every call, nothing carries over from the previous geometry."""
+    m = build("b0", seed=43)
+    for i, (H, W) in enumerate(sizes):
+        imgs = synth.synth_clip(1, 4, H, W, seed=50 + i)
+        metas = synth.img_metas(1, H, W)
+        got = m.predict_labels(imgs, metas).clone()
+        want = build("b0", seed=43).predict_labels(imgs, metas)
+        assert torch.equal(got, want), (i, H, W)

@@ -47,6 +47,11 @@ class GraphedClips:
         with torch.cuda.graph(self.graph):
             self.labels = run_pass()
         self.kernels_per_replay = _abi.n_launches - n0
+        for ws in model.workspaces():                            # the graph replays on these addresses: never free them
+            ws.pin()
+        # ... and on the folded weights of the plans it was captured with: keep them alive even if a later
+        # load_state_dict() rebuilds the plans (the owner is expected to drop this graph then: invalidate_graphs())
+        self._plans = (getattr(model.backbone, "_plan", None), getattr(model.decode_head, "_plan", None))
 
     def load(self, imgs):
         """Copy a list of T (B,3,H,W) tensors (host, ideally pinned, or device) into the static input buffer."""

@@ -122,7 +122,7 @@ class FrameShardedRunner:
                 ops.gemm(t.reshape(-1, t.shape[3]), P["pw"][i], out16=p)
                 proj.append(p)
         else:
-            h, w = H // 4, W // 4
+            h, w = (H - 1) // 4 + 1, (W - 1) // 4 + 1              # OverlapPatchEmbed k7 s4 p3 (mix_transformer.py:173-195): same on every rank
         h2, w2 = h // 2, w // 2
         HW = h2 * w2
         Hp, Wp = (h2 + 6) // 7 * 7, (w2 + 6) // 7 * 7
@@ -207,6 +207,8 @@ class GraphedFrameShard:
         with torch.cuda.graph(self.graph):
             self.labels = runner.run(self.frames)
         self.kernels_per_replay = _abi.n_launches - n0
+        for ws in [runner.ws] + runner.model.workspaces():       # the graph replays on these addresses: never free them
+            ws.pin()
 
     def replay(self):
         self.graph.replay()

@@ -11,6 +11,8 @@
   * final bilinear resize + softmax + argmax (:373-377, :542, :564) is one kernel (softmax is
     monotone, so the argmax is taken on the interpolated logits).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -44,6 +46,19 @@ class EncoderDecoder_clips(nn.Module):
         self._ws = Workspace()
         for m in self.modules():
             m.training = False
+        self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_graphs())
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_graphs()                                 # .cuda() / .to(): the captured passes read the old tensors
+        return super()._apply(fn, *a, **k)
+
+    def workspaces(self):
+        """Every Workspace a forward pass of this model touches (CUDA-graph owners pin them)."""
+        out = [self._ws]
+        for m in (self.backbone, self.decode_head):
+            if hasattr(m, "_ws"):
+                out.append(m._ws)
+        return out
 
     # ------------------------------------------------------------------ BaseSegmentor surface
     @property
@@ -215,7 +230,50 @@ class EncoderDecoder_clips(nn.Module):
         from .graph import GraphedClips
         return GraphedClips(self, B, T, H, W, img_meta, rescale, head_kw)
 
+    # ------------------------------------------------------------------ CUDA-graph cache behind the mmseg call
+    GRAPH_CACHE_SIZE = 4                                          # geometries kept captured (least recently used is dropped)
+    GRAPH_CACHE_AFTER = 2                                         # capture on the n-th call with the same geometry
+
+    def _cached_graph(self, img, img_meta, rescale, head_kw):
+        """The captured pass for this call's geometry, or None (eager).  ``model(img=..., return_loss=False)`` launches
+        ~100 kernels; from the second call with the same (B, T, H, W, ori_shape, flip) on, the pass is captured once
+        (``GraphedClips``) and every later call is one H2D copy per frame stack + one cudaGraphLaunch.  Heads that read
+        per-call host state (CFFM++ prototypes from files, prototype generation) always run eagerly."""
+        head = self.decode_head
+        if (not getattr(self, "graph_cache", True) or head_kw or getattr(head, "WITH_PROTOTYPES", False) or
+                not getattr(head, "FUSED_TAIL", True) or os.environ.get("CFFM_GRAPH_CACHE", "1") == "0"):
+            return None
+        frames = img if isinstance(img, (list, tuple)) else list(img.unbind(1))
+        T, (B, C, H, W) = len(frames), tuple(frames[0].shape)
+        m0 = img_meta[0]
+        key = (B, T, C, H, W, bool(rescale), tuple(m0["ori_shape"][:2]), bool(m0.get("flip", False)), m0.get("flip_direction"))
+        cache = self.__dict__.setdefault("_graphs", {})
+        seen = self.__dict__.setdefault("_graph_seen", {})
+        g = cache.get(key)
+        if g is None:
+            seen[key] = seen.get(key, 0) + 1
+            if seen[key] < self.GRAPH_CACHE_AFTER:
+                return None
+            if len(seen) > 64:
+                seen.clear()
+            if len(cache) >= self.GRAPH_CACHE_SIZE:
+                cache.pop(next(iter(cache)))
+            g = self.make_graphed(B, T, H, W, [dict(m) for m in img_meta], rescale)
+        else:
+            cache.pop(key)                                       # re-insert: most recently used last
+        cache[key] = g
+        return g
+
+    def invalidate_graphs(self):
+        """Drop every captured pass (new weights change the folded plans the graphs read)."""
+        self.__dict__.pop("_graphs", None)
+        self.__dict__.pop("_graph_seen", None)
+
     def simple_test(self, img, img_meta, rescale=True, **head_kw):
         """encoder_decoder.py:554-572: list of B (H,W) int64 numpy label maps."""
-        labels = self.predict_labels(img, img_meta, rescale, **head_kw)
+        g = self._cached_graph(img, img_meta, rescale, head_kw)
+        if g is not None:
+            labels = g(img if isinstance(img, (list, tuple)) else list(img.unbind(1)))
+        else:
+            labels = self.predict_labels(img, img_meta, rescale, **head_kw)
         return list(labels.cpu().numpy())

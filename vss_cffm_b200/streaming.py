@@ -79,6 +79,8 @@ class VideoStream:
                 with torch.cuda.graph(g):
                     out = self._step(self.static_in, i)
                 self.graphs[phase] = (g, out)
+                for ws in [self.ws] + self.model.workspaces():   # the graphs replay on these addresses: never free them
+                    ws.pin()
             g, labels = self.graphs[phase]
             g.replay()
         self.kv[i] = i % hist
