@@ -64,3 +64,13 @@ for _ in range(3):
     fn()
 torch.cuda.synchronize()
 print("ok", which)
+if os.environ.get("TIME"):
+    ts = []
+    for _ in range(30):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    print(f"{which}: median {ts[len(ts) // 2]:.2f} us, min {ts[0]:.2f} us (cold L2, CUDA events)")

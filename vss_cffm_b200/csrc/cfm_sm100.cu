@@ -12,20 +12,25 @@
 //     small maps: 5x5 / 7x7 / 5x5 / 3x3 boxes at (i-2, j-2) / (i-3, j-3) / (2i-2, 2j-2) / (3i-1, 3j-1); the TMA
 //     out-of-bounds zero fill IS Unfold's zero padding, and the -100 mask (:433-446, :481-492) follows from the same
 //     coordinates (K = V = 0 there, so exp(-100) relative weight is replaced by an exact 0: difference < 4e-44).
-// Every key row is 128 bytes = the 64 channels of the head pair, 128-byte swizzled, i.e. directly a tcgen05 operand.
+// Every key row is 128 bytes = the 64 channels of the head pair, 128-byte swizzled, i.e. directly a tcgen05 operand; the
+// five boxes are packed back to back (a TMA destination only needs 128-byte alignment: the swizzle is a function of the
+// shared-memory address, so a box may start inside a 1024-byte swizzle atom -- verified bit for bit on B200).
 //
 // Per item:
-//   S[128 x N] = Qbd K^T   M = 128 rows = (head 0: 49 queries | pad to 64 | head 1: 49 queries | pad), K = 64 channels with
-//                          Q block-diagonal (head-0 rows carry zeros in head 1's channels and vice versa), so ONE
-//                          M = 128 MMA computes both heads at the tensor-core cost of two M = 64 ones.
-//   softmax                8 warps, thread = (row, half of each 64-key chunk); logits t = S + bias / scale straight out of
-//                          TMEM (one FHFMA per element: fp16 bias operand, fp32 accumulator), exact two-pass row
-//                          maximum, p = 2^((t - m) scale log2 e) -> fp16 P chunks in shared memory (swizzled A operand)
-//   O[128 x 64] += P V     B = V chunk MN-major as loaded; only the diagonal 32-column blocks are read back
-//   epilogue               O / rowsum -> fp16, window_reverse + crop (:812-821) fused into the store
-// Warp roles: 0..7 softmax / epilogue, 8 producer (TMA + block-diagonal Q through cp.async), 9 TMEM allocator + MMA issuer.
-// K, Q and V are single-buffered: K/Q of item i+1 are loaded while the softmax of item i runs, V after P V of item i.
+//   S[128 x 288] = Qbd K^T  M = 128 rows = (head 0: 49 queries | pad to 64 | head 1: 49 queries | pad), K = 64 channels with
+//                           Q block-diagonal (head-0 rows carry zeros in head 1's channels and vice versa), so ONE
+//                           M = 128 MMA computes both heads at the tensor-core cost of two M = 64 ones.
+//   softmax                 16 warps, thread = (row, quarter of each 64-key chunk); logits t = S + bias / scale straight out
+//                           of TMEM (one FHFMA per element: fp16 bias operand, fp32 accumulator), exact two-pass row
+//                           maximum, p = 2^((t - m) scale log2 e) -> fp16 P chunks in shared memory (swizzled A operand)
+//   O[128 x 64] += P V      B = V chunk MN-major as loaded; only the diagonal 32-column blocks are read back
+//   epilogue                O / rowsum -> fp16, window_reverse + crop (:812-821) fused into the store
+// Warp roles: 0..15 softmax / epilogue, 16 producer (TMA, block-diagonal Q through cp.async, the item's key mask), 17 TMEM
+// allocator + MMA issuer.  K and Q are single-buffered (those of item i+1 are loaded while the softmax of item i runs), V
+// is double-buffered (loaded a whole item ahead), O is double-buffered in TMEM, P goes through a two-chunk ring.
 #include <cuda.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -36,405 +41,537 @@ namespace {
 constexpr int WS = 7, RING = 3, HALO = WS + 2 * RING, NHALO = HALO * HALO;      // 13, 169
 constexpr int CQKV = 768, CKV = 512, CPAIR = 64;                                // channels: qkv row, pooled K|V row, head pair
 constexpr int ROWB = 128;                                                       // bytes per key / query row in shared memory
-constexpr int SM_WARPS = 8, CFM_THREADS = (SM_WARPS + 2) * 32;
-constexpr int P_RING = 2, P_CHUNK_BYTES = 128 * ROWB;
+constexpr int SM_WARPS = 16, CFM_THREADS = (SM_WARPS + 3) * 32;   // + producer, P V issuer, Q K^T issuer
+constexpr int P_RING = 3, P_COLS = 32;                                          // P chunks (64 keys = 32 packed cells) in TMEM
 constexpr int Q_BYTES = 128 * ROWB;
 constexpr float LOG2E = 1.4426950408889634f;
+#define CFM_PROF(slot) do { if (p.prof != nullptr && it < 8) p.prof[(blockIdx.x * 8 + it) * 32 + (slot)] = clock64(); } while (0)
 
-// Key-row layout of the assembled sequence.  TIGHT packs the five boxes back to back (TMA destinations are 128-byte
-// aligned; the 128-byte swizzle is a function of the shared-memory address, so a box may start inside a 1024-byte
-// swizzle atom).  The ALIGNED variant starts every box on a 1024-byte boundary (rows padded with masked zero keys).
-template <bool ALIGNED>
-struct Lay {
-  static constexpr int R1 = ALIGNED ? 176 : NHALO;           // pooled target level, 5 x 5
-  static constexpr int R2 = R1 + (ALIGNED ? 32 : 25);        // reference frame 0, 7 x 7
-  static constexpr int R3 = R2 + (ALIGNED ? 56 : 49);        // reference frame 1, 5 x 5
-  static constexpr int R4 = R3 + (ALIGNED ? 32 : 25);        // reference frame 2, 3 x 3
-  static constexpr int REND = R4 + 9;
-  static constexpr int NPAD = ALIGNED ? 320 : 288;           // MMA N (two halves, each a multiple of 16)
-  static constexpr int BPITCH = ALIGNED ? 328 : 296;         // bias row pitch (halves): conflict-free 16-byte LDS per row
-  static constexpr int NCH = (NPAD + 63) / 64;               // 64-key P chunks (the last one of TIGHT holds 32 keys)
-  static constexpr int KV_BYTES = NPAD * ROWB;
-  static constexpr int TX_BYTES = (NHALO + 25 + 49 + 25 + 9) * ROWB;
-  static constexpr int BIAS_BYTES = 2 * 49 * BPITCH * 2;
-  static constexpr int SMEM = 2 * KV_BYTES + Q_BYTES + P_RING * P_CHUNK_BYTES + BIAS_BYTES + 2 * NPAD * 4 /*mask*/ +
-                              2 * 2 * 2 * 128 * 4 /*row max / sum exchange*/ + 256 /*barriers*/ + 1024 /*align slack*/;
-  static constexpr int TMEM_O = NPAD;                        // two O buffers of 64 columns behind S
-};
+// Key-row layout of the assembled sequence: halo | pooled target 5x5 | reference 0 7x7 | reference 1 5x5 | reference 2 3x3
+constexpr int R1 = NHALO, R2 = R1 + 25, R3 = R2 + 49, R4 = R3 + 25, REND = R4 + 9;   // 169, 194, 243, 268, 277
+constexpr int NPAD = 288;                                    // MMA N (two halves of 144); rows >= 277 are zero keys with a -inf bias
+constexpr int BPITCH = 296;                                  // bias row pitch (halves): conflict-free 16-byte LDS per row
+constexpr int NCH = (NPAD + 63) / 64;                        // 64-key P chunks, the last one holds 32 keys
+constexpr int NCH_A = 2, N_A = NCH_A * 64, N_B = NPAD - N_A; // S is produced and released in two halves: columns [0,128) and [128,288)
+constexpr int X_FLOATS = 2 * 4 * 128;                        // [max | sum][column quarter][row]
+constexpr int KV_BYTES = NPAD * ROWB;
+constexpr int TX_BYTES = REND * ROWB;
+constexpr int BIAS_BYTES = 2 * 49 * BPITCH * 2;
+constexpr int CFM_SMEM = 3 * KV_BYTES + 2 * Q_BYTES + BIAS_BYTES + 2 * (NPAD + 4) * 4 /*mask + item coordinates*/ +
+                         2 * X_FLOATS * 4 /*row max / sum exchange, two item parities*/ + 256 /*barriers*/ + 1024 /*align slack*/;
+constexpr int TMEM_O = NPAD;                                 // two O buffers of 64 columns behind S ...
+constexpr int TMEM_P = TMEM_O + 2 * CPAIR;                   // ... and the P ring behind them: 288 + 128 + 96 = 512 columns
+static_assert(TMEM_P + P_RING * P_COLS <= 512, "TMEM budget");
+static_assert(CFM_SMEM <= 232448, "shared memory budget of one CTA per SM");
 
 struct CfmParams {
   const __half* qkv_a;      // [B, Hp+6, Wp+6, 768] apron layout
   const __half* bias_tab;   // [8 heads, 49, BPITCH] fp16, bias / scale in the kernel's key order, -inf on unused columns
   __half* out;              // [B, H, W, 256]
-  __half* dump;             // test hook: [items of head pair 0.., 2, NPAD, 64] assembled K and V tiles (or null)
+  __half* dump;             // test hook: [4 head pairs, B nW items, 2, NPAD, 64] assembled K and V tiles (or null)
+  long long* prof;          // bring-up hook: per CTA / item / event SM clock stamps [grid, 8, 32] (or null)
   int B, H, W, nWh, nWw;
   float scale_log2e;
 };
 
-// Additive mask (in accumulator units) of key row n for window (wi, wj): 0, or -inf for an nn.Unfold zero-padding
-// position of a pooled level.  Halo rows and unused rows are 0 (unused rows carry a -inf bias).
-template <bool AL>
-__device__ __forceinline__ float key_mask(int n, int wi, int wj, int nWh, int nWw) {
-  using L = Lay<AL>;
-  int m, kc, st, f;
-  if (n >= L::R1 && n < L::R1 + 25) { m = n - L::R1; kc = 5; st = 1; f = 1; }
-  else if (n >= L::R2 && n < L::R2 + 49) { m = n - L::R2; kc = 7; st = 1; f = 1; }
-  else if (n >= L::R3 && n < L::R3 + 25) { m = n - L::R3; kc = 5; st = 2; f = 2; }
-  else if (n >= L::R4 && n < L::R4 + 9) { m = n - L::R4; kc = 3; st = 3; f = 3; }
-  else return 0.f;
-  const int y = st * wi + m / kc - kc / 2, x = st * wj + m % kc - kc / 2;
-  return (y >= 0 && y < f * nWh && x >= 0 && x < f * nWw) ? 0.f : -INFINITY;
+struct CfmBars {
+  uint64_t *s_full, *s_empty, *m_full, *p_full, *p_empty, *o_full, *o_empty;
+};
+
+// Issue (no wait) the TMEM load of this thread's piece of chunk C: S[row, 64 C + cq w .. + w), w = 16 (8 in the last chunk)
+template <int C>
+__device__ __forceinline__ void cfm_issue_load(uint32_t lane_addr, int cq, uint32_t* u) {
+  if (C * 64 + 64 <= NPAD) ptx::tmem_ld_32x32b_x16(lane_addr + C * 64 + cq * 16, u);
+  else ptx::tmem_ld_32x32b_x8(lane_addr + C * 64 + cq * 8, u);
 }
 
-// ---- softmax / epilogue role, G = which half of every 64-key chunk this warp owns (compile time: all column offsets
-// are immediates)
-template <bool AL, int G>
-__device__ __forceinline__ void softmax_role(const CfmParams& p, uint8_t* sP, const __half* sBias, float* sMask, float* sX,
-                                             uint64_t* s_full, uint64_t* s_empty, uint64_t* p_full, uint64_t* p_empty,
-                                             uint64_t* o_full, uint64_t* o_empty, uint32_t tmem_base, int hp, int slot,
-                                             int nslots) {
-  using L = Lay<AL>;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wq = warp & 3;                                   // TMEM lane quarter
-  const int row = wq * 32 + lane;                            // row of S = TMEM lane
-  const int hl = row >> 6, q = row & 63;                     // head of the pair, query index (>= 49: padding)
-  const int qc = q < 49 ? q : 48;
-  const __half* brow = sBias + (hl * 49 + qc) * L::BPITCH;
-  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-  const int stid = threadIdx.x;                              // 0..255 among the softmax warps
-  const int nW = p.nWh * p.nWw, n_items = p.B * nW;
-  const float scl = p.scale_log2e;
-  const int bar_pair = 1 + wq;                               // named barrier of the two warps that share these 32 rows
-
-  uint32_t it = 0;
-  for (int item = slot; item < n_items; item += nslots, ++it) {
-    const int b = item / nW, w = item - b * nW, wi = w / p.nWw, wj = w - wi * p.nWw;
-    float* mask = sMask + (it & 1u) * L::NPAD;
-    for (int n = stid; n < L::NPAD; n += SM_WARPS * 32) mask[n] = key_mask<AL>(n, wi, wj, p.nWh, p.nWw);
-    asm volatile("bar.sync 5, 256;" ::: "memory");
-
-    ptx::mbar_wait(s_full, it & 1u);
-    ptx::tc_fence_after();
-
-    // t[j] = S[row, col0 + j] + bias / scale (+ mask): the logit divided by the (positive) attention scale
-    auto logits = [&](int col0, int wcol, float* t) {
-      uint32_t v[32];
-      if (wcol == 32) ptx::tmem_ld_32x32b_x32(lane_addr + col0, v);
-      else ptx::tmem_ld_32x32b_x16(lane_addr + col0, v);
-      const uint4* bp = reinterpret_cast<const uint4*>(brow + col0);
-      uint4 bw[4];
+// v[j] = u[j] (+ mask): raw accumulator, nn.Unfold padding positions of the pooled levels at -inf.  Chunks 0 and 1 hold halo
+// keys only (never masked); the mask of a halo key in the later chunks is 0.
+template <int C, int WCOL>
+__device__ __forceinline__ void cfm_masked(const uint32_t* u, const float* mask_piece, float* v) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j * 8 < wcol) bw[j] = bp[j];
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j * 8 < wcol) {
-          const uint32_t ww[4] = {bw[j].x, bw[j].y, bw[j].z, bw[j].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            ptx::fhfma2(ww[e], __uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]), t[j * 8 + 2 * e],
-                        t[j * 8 + 2 * e + 1]);
-        }
-      }
-      if (col0 + wcol > L::R1) {                             // pooled levels: nn.Unfold padding positions are masked
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j * 4 < wcol) {
-            const float4 mk = *reinterpret_cast<const float4*>(mask + col0 + j * 4);
-            t[j * 4] += mk.x; t[j * 4 + 1] += mk.y; t[j * 4 + 2] += mk.z; t[j * 4 + 3] += mk.w;
-          }
-        }
-      }
-    };
-
-    // ---- pass 1: exact row maximum
-    float mx = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < L::NCH; ++c) {
-      const int wcol = (c * 64 + 64 <= L::NPAD) ? 32 : 16;
-      const int col0 = c * 64 + G * wcol;
-      float t[32];
-      logits(col0, wcol, t);
-      float m0 = t[0], m1 = t[1], m2 = t[2], m3 = t[3];
-#pragma unroll
-      for (int j = 4; j < 32; j += 4) {
-        if (j < wcol) { m0 = fmaxf(m0, t[j]); m1 = fmaxf(m1, t[j + 1]); m2 = fmaxf(m2, t[j + 2]); m3 = fmaxf(m3, t[j + 3]); }
-      }
-      mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-    }
-    float* xm = sX + (it & 1u) * 512;                        // [max | sum][G][128 rows]
-    xm[G * 128 + row] = mx;
-    asm volatile("bar.sync %0, 64;" ::"r"(bar_pair) : "memory");
-    mx = fmaxf(mx, xm[(G ^ 1) * 128 + row]);                 // the halo keys are never masked: finite
-    const float msc = mx * scl;
-
-    // ---- pass 2: p = 2^((t - m) scale log2 e), row sum, fp16 P chunks in the swizzled A-operand layout
-    float sum = 0.f;
-#pragma unroll
-    for (int c = 0; c < L::NCH; ++c) {
-      const int wcol = (c * 64 + 64 <= L::NPAD) ? 32 : 16;
-      const int col0 = c * 64 + G * wcol;
-      const uint32_t gc = it * L::NCH + c, ps = gc % P_RING;
-      float t[32];
-      logits(col0, wcol, t);
-      if (c == L::NCH - 1) {                                 // S of this item has been read for the last time
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(s_empty);
-      }
-      uint32_t hh[16];
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (2 * j < wcol) {
-          const float p0 = ptx::ex2_approx(fmaf(t[2 * j], scl, -msc));
-          const float p1 = ptx::ex2_approx(fmaf(t[2 * j + 1], scl, -msc));
-          s0 += p0; s1 += p1;
-          hh[j] = pack_half2(p0, p1);
-        }
-      }
-      sum += s0 + s1;
-      ptx::mbar_wait(&p_empty[ps], ((gc / P_RING) & 1u) ^ 1u);
-      uint8_t* prow = sP + ps * P_CHUNK_BYTES + row * ROWB;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {                          // 8 keys = one 16-byte piece
-        if (g * 8 < wcol) {
-          const int piece = G * (wcol / 8) + g;
-          *reinterpret_cast<uint4*>(prow + ((piece ^ (row & 7)) << 4)) =
-              make_uint4(hh[4 * g], hh[4 * g + 1], hh[4 * g + 2], hh[4 * g + 3]);
-        }
-      }
-      ptx::fence_proxy_async();                              // generic-proxy smem writes -> visible to the MMA (async proxy)
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&p_full[ps]);
-    }
-    xm[256 + G * 128 + row] = sum;
-    asm volatile("bar.sync %0, 64;" ::"r"(bar_pair) : "memory");
-    const float inv = 1.f / (xm[256 + row] + xm[256 + 128 + row]);    // same order in both threads of the row
-
-    // ---- epilogue: O[row, 32 hl + 16 G .. +16) / rowsum -> fp16 -> out (window_reverse + crop)
-    const uint32_t ob = it & 1u;
-    ptx::mbar_wait(&o_full[ob], (it >> 1) & 1u);
-    ptx::tc_fence_after();
-    uint32_t o[16];
-    ptx::tmem_ld_32x32b_x16(lane_addr + L::TMEM_O + ob * 64 + hl * 32 + G * 16, o);
-    ptx::tmem_ld_wait();
-    ptx::tc_fence_before();
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&o_empty[ob]);
-    const int y = WS * wi + q / WS, x = WS * wj + q % WS;
-    if (q < 49 && y < p.H && x < p.W) {
-      __half* dst = p.out + ((static_cast<int64_t>(b) * p.H + y) * p.W + x) * 256 + hp * CPAIR + hl * 32 + G * 16;
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        uint4 wv;
-        wv.x = pack_half2(__uint_as_float(o[g * 8]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
-        wv.y = pack_half2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
-        wv.z = pack_half2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
-        wv.w = pack_half2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
-        *reinterpret_cast<uint4*>(dst + g * 8) = wv;
-      }
+  for (int j = 0; j < WCOL / 4; ++j) {
+    if (C * 64 + 64 > R1) {
+      const float4 mk = *reinterpret_cast<const float4*>(mask_piece + j * 4);
+      v[j * 4] = __uint_as_float(u[j * 4]) + mk.x; v[j * 4 + 1] = __uint_as_float(u[j * 4 + 1]) + mk.y;
+      v[j * 4 + 2] = __uint_as_float(u[j * 4 + 2]) + mk.z; v[j * 4 + 3] = __uint_as_float(u[j * 4 + 3]) + mk.w;
+    } else {
+      v[j * 4] = __uint_as_float(u[j * 4]); v[j * 4 + 1] = __uint_as_float(u[j * 4 + 1]);
+      v[j * 4 + 2] = __uint_as_float(u[j * 4 + 2]); v[j * 4 + 3] = __uint_as_float(u[j * 4 + 3]);
     }
   }
 }
 
-template <bool AL>
+// ---- softmax / epilogue role.  16 warps: thread = (row of S, quarter cq of every 64-key chunk).  All 16 warps run the SAME
+// instruction stream (cq is a run-time, warp-uniform offset): with one template instantiation per quarter the four warps
+// of a scheduler executed four different 13 KB code streams and the kernel was bound by instruction fetch (ncu: 7.6
+// warps stalled on "no instruction" per issued instruction).  Machine facts this layout follows (measured on B200:
+// tools/micro and the in-kernel timeline of tools/cfm_timeline.py):
+//   * tcgen05.ld costs ~3 cycles per column per warp and overlaps across the warps of a TMEM lane quarter: every load is
+//     issued one chunk ahead of its use (two register sets), so its latency hides behind the exp2 work of the chunk before;
+//   * fence.proxy.async is a ~110-cycle MEMBAR that serialises across warps, and an mbarrier wait costs ~100 cycles even
+//     when the phase is already complete: P therefore never goes through shared memory (tcgen05.st into TMEM, A operand of
+//     a TS-mode MMA), and there is one mbarrier wait per chunk, placed ahead of the math;
+//   * MUFU.EX2 (16 lanes / clock / SM: 512 cycles per 64-key chunk) is the floor of pass 2.
+__device__ __forceinline__ void softmax_role(const CfmParams& p, const __half* sBias, const float* sMask, float* sX,
+                                          const CfmBars& bar, uint32_t tmem_base, int hp, int slot, int nslots) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wq = warp & 3, cq = warp >> 2;                   // TMEM lane quarter, column quarter of every chunk
+  const int row = wq * 32 + lane;                            // row of S = TMEM lane
+  const int hl = row >> 6, q = row & 63;                     // head of the pair, query index (>= 49: padding)
+  const int qc = q < 49 ? q : 48;
+  const __half* brow = sBias + (hl * 49 + qc) * BPITCH;
+  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+  const int stid = threadIdx.x;
+  const int n_items = p.B * p.nWh * p.nWw;
+  const float scl = p.scale_log2e;
+  const int bar_rows = 1 + wq;                               // named barrier of the four warps that share these 32 rows
+
+  // Largest bias of this thread's piece of every chunk (a constant of the head pair).  Pass 1 then needs no bias at all:
+  // max_k (S_k + bias_k) <= max over pieces of (max_k S_k + max_k bias_k) =: m, an upper bound that is exact up to the
+  // spread of the bias inside a 16-key piece.  Softmax is invariant to the shift; p = 2^((t - m) ...) <= 1 always.
+  float bmax[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int wcol = (c * 64 + 64 <= NPAD) ? 16 : 8, col0 = c * 64 + cq * wcol;
+    float m = -INFINITY;
+    for (int j = 0; j < wcol; ++j) m = fmaxf(m, __half2float(brow[col0 + j]));
+    bmax[c] = m;                                             // -inf for a piece of unused key rows only
+  }
+
+  // epilogue of an item: O[row, 32 hl + 8 cq .. +8) / rowsum -> fp16 -> out (window_reverse + crop, :812-821).  (Running it
+  // one item late, between the two passes of the next item, was measured slower: it then sits on the path to the first P chunk.)
+  auto epilogue = [&](uint32_t e_it, int b, int wi, int wj, float inv) {
+    const uint32_t ob = e_it & 1u;
+    ptx::mbar_wait(&bar.o_full[ob], (e_it >> 1) & 1u);
+    ptx::tc_fence_after();
+    { const uint32_t it = e_it; if (stid == 0) CFM_PROF(17); }
+    uint32_t o[8];
+    ptx::tmem_ld_32x32b_x8(lane_addr + TMEM_O + ob * 64 + hl * 32 + cq * 8, o);
+    ptx::tmem_ld_wait();
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&bar.o_empty[ob]);
+    { const uint32_t it = e_it; if (stid == 0) CFM_PROF(18); }
+    const int y = WS * wi + q / WS, x = WS * wj + q % WS;
+    if (q < 49 && y < p.H && x < p.W) {
+      __half* dst = p.out + ((static_cast<int64_t>(b) * p.H + y) * p.W + x) * 256 + hp * CPAIR + hl * 32 + cq * 8;
+      uint4 wv;
+      wv.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+      wv.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+      wv.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+      wv.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+      *reinterpret_cast<uint4*>(dst) = wv;
+    }
+    { const uint32_t it = e_it; if (stid == 0) CFM_PROF(19); }
+  };
+
+  uint32_t it = 0;
+  float pinv = 0.f;
+  for (int item = slot; item < n_items; item += nslots, ++it) {
+    const float* mask = sMask + (it & 1u) * (NPAD + 4);
+    float* xm = sX + (it & 1u) * X_FLOATS;
+    uint32_t sb[2][16];                                      // two register sets: chunk C lives in sb[C & 1]
+    if (stid == 0) CFM_PROF(8);
+    ptx::mbar_wait(&bar.m_full[it & 1u], (it >> 1) & 1u);
+    // {clip, window row, window column} of this item: read NOW -- after the last read of S the producer may rewrite the buffer
+    const int4 info = *reinterpret_cast<const int4*>(mask + NPAD);
+    const int cb = info.x, cwi = info.y, cwj = info.z;
+    ptx::mbar_wait(&bar.s_full[0], it & 1u);
+    ptx::tc_fence_after();
+    if (stid == 0) CFM_PROF(9);
+    cfm_issue_load<0>(lane_addr, cq, sb[0]);
+
+    // ---- pass 1: upper bound of the row maximum
+    float mx = -INFINITY;
+    auto pass1 = [&](auto cc) {
+      constexpr int C = decltype(cc)::value;
+      constexpr int WCOL = (C * 64 + 64 <= NPAD) ? 16 : 8;
+      ptx::tmem_ld_wait();                                   // chunk C has landed
+      if (C + 1 == NCH_A) {                                  // the next chunk is the first of the second half of S
+        ptx::mbar_wait(&bar.s_full[1], it & 1u);
+        ptx::tc_fence_after();
+      }
+      if (C + 1 < NCH) cfm_issue_load<C + 1>(lane_addr, cq, sb[(C + 1) & 1]);
+      else cfm_issue_load<0>(lane_addr, cq, sb[(C + 1) & 1]);      // chunk 0 again, for pass 2
+      float v[WCOL];
+      cfm_masked<C, WCOL>(sb[C & 1], mask + C * 64 + cq * WCOL, v);
+      float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]);
+#pragma unroll
+      for (int j = 4; j < WCOL; j += 4) { m0 = fmaxf(m0, fmaxf(v[j], v[j + 1])); m1 = fmaxf(m1, fmaxf(v[j + 2], v[j + 3])); }
+      mx = fmaxf(mx, fmaxf(m0, m1) + bmax[C]);
+    };
+    pass1(std::integral_constant<int, 0>{}); pass1(std::integral_constant<int, 1>{}); pass1(std::integral_constant<int, 2>{});
+    pass1(std::integral_constant<int, 3>{}); pass1(std::integral_constant<int, 4>{});
+    xm[cq * 128 + row] = mx;
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_rows) : "memory");
+    mx = fmaxf(fmaxf(xm[row], xm[128 + row]), fmaxf(xm[256 + row], xm[384 + row]));   // the halo keys are never masked: finite
+    const float msc = mx * scl;
+    if (stid == 0) CFM_PROF(10);
+
+    // ---- pass 2: p = 2^((S + bias / scale - m) scale log2 e), row sum, packed fp16 P chunks into tensor memory.
+    // Chunk C of pass 2 sits in sb[(NCH + C) & 1] (pass 1 left chunk 0 in flight in sb[NCH & 1]).
+    float sum0 = 0.f, sum1 = 0.f;
+    auto pass2 = [&](auto cc) {
+      constexpr int C = decltype(cc)::value;
+      constexpr int WCOL = (C * 64 + 64 <= NPAD) ? 16 : 8;
+      const int col0 = C * 64 + cq * WCOL;
+      const uint32_t gc = it * NCH + C, ps = gc % P_RING;
+      ptx::tmem_ld_wait();                                   // chunk C has landed
+      if (C + 1 < NCH) cfm_issue_load<C + 1>(lane_addr, cq, sb[(NCH + C + 1) & 1]);
+      if (C == NCH_A - 1 || C == NCH - 1) {                  // this half of S has been read for the last time
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar.s_empty[C == NCH - 1 ? 1 : 0]);
+      }
+      // the ring slot is almost always free already; the probe is issued here and its ~100-cycle latency hides behind the math
+      const bool slot_free = ptx::mbar_test_wait(&bar.p_empty[ps], ((gc / P_RING) & 1u) ^ 1u);
+      uint4 bw[WCOL / 8];
+#pragma unroll
+      for (int j = 0; j < WCOL / 8; ++j) bw[j] = reinterpret_cast<const uint4*>(brow + col0)[j];
+      float v[WCOL];
+      cfm_masked<C, WCOL>(sb[(NCH + C) & 1], mask + col0, v);
+      uint32_t hh[WCOL / 2];
+#pragma unroll
+      for (int j = 0; j < WCOL / 8; ++j) {
+        const uint32_t ww[4] = {bw[j].x, bw[j].y, bw[j].z, bw[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float t0, t1;
+          ptx::fhfma2(ww[e], v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1], t0, t1);      // S + bias / scale: one FHFMA per element
+          const float p0 = ptx::ex2_approx(fmaf(t0, scl, -msc));
+          const float p1 = ptx::ex2_approx(fmaf(t1, scl, -msc));
+          sum0 += p0; sum1 += p1;
+          hh[j * 4 + e] = pack_half2(p0, p1);
+        }
+      }
+      if (!slot_free) ptx::mbar_wait(&bar.p_empty[ps], ((gc / P_RING) & 1u) ^ 1u);
+      ptx::tc_fence_after();
+      // P stays in tensor memory (A operand of the P V MMA): packed fp16 pairs, 8 keys = 4 cells.  Published at once: P V of
+      // the last chunks is on the path to the epilogue (publishing one chunk late was measured slower).
+      const uint32_t pa = lane_addr + TMEM_P + ps * P_COLS + cq * (WCOL / 2);
+      if (WCOL == 16) ptx::tmem_st_32x32b_x8(pa, hh);
+      else ptx::tmem_st_32x32b_x4(pa, hh);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar.p_full[ps]);
+    };
+    pass2(std::integral_constant<int, 0>{}); pass2(std::integral_constant<int, 1>{}); pass2(std::integral_constant<int, 2>{});
+    pass2(std::integral_constant<int, 3>{}); pass2(std::integral_constant<int, 4>{});
+    if (stid == 0) CFM_PROF(11);
+    xm[512 + cq * 128 + row] = sum0 + sum1;
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_rows) : "memory");
+    pinv = 1.f / ((xm[512 + row] + xm[640 + row]) + (xm[768 + row] + xm[896 + row]));   // same order in all four threads
+    if (stid == 0) CFM_PROF(12);
+    epilogue(it, cb, cwi, cwj, pinv);
+  }
+}
+
 __global__ void __launch_bounds__(CFM_THREADS, 1)
 cfm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmL1,
                         const __grid_constant__ CUtensorMap tmL2, const __grid_constant__ CUtensorMap tmL3,
                         const __grid_constant__ CUtensorMap tmL4, const CfmParams p) {
-  using L = Lay<AL>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sK = smem;
-  uint8_t* sV = sK + L::KV_BYTES;
-  uint8_t* sQ = sV + L::KV_BYTES;
-  uint8_t* sP = sQ + Q_BYTES;
-  __half* sBias = reinterpret_cast<__half*>(sP + P_RING * P_CHUNK_BYTES);
-  float* sMask = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sBias) + L::BIAS_BYTES);
-  float* sX = sMask + 2 * L::NPAD;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 2 * 512);
-  uint64_t* k_full = bars + 0;     // TMA -> MMA: K tile landed (transaction bytes)
-  uint64_t* q_full = bars + 1;     // producer warp -> MMA: block-diagonal Q written
-  uint64_t* kq_empty = bars + 2;   // MMA -> producer: Q K^T retired, K and Q may be overwritten
-  uint64_t* v_full = bars + 3;     // TMA -> MMA: V tile landed
-  uint64_t* v_empty = bars + 4;    // MMA -> producer: P V retired
-  uint64_t* s_full = bars + 5;     // MMA -> softmax: S complete
-  uint64_t* s_empty = bars + 6;    // softmax (8 warps) -> MMA: S read for the last time
-  uint64_t* p_full = bars + 7;     // [P_RING] softmax (8 warps) -> MMA: P chunk written
-  uint64_t* p_empty = bars + 9;    // [P_RING] MMA -> softmax: P chunk consumed
-  uint64_t* o_full = bars + 11;    // [2] MMA -> epilogue: O complete
-  uint64_t* o_empty = bars + 13;   // [2] epilogue (8 warps) -> MMA: O read out
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 16);
+  uint8_t* sV = sK + KV_BYTES;                                 // 2 buffers
+  uint8_t* sQ = sV + 2 * KV_BYTES;                             // 2 buffers
+  __half* sBias = reinterpret_cast<__half*>(sQ + 2 * Q_BYTES);
+  float* sMask = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sBias) + BIAS_BYTES);
+  float* sX = sMask + 2 * (NPAD + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 2 * X_FLOATS);
+  uint64_t* k_full = bars + 0;     // TMA -> Q K^T issuer: K tile landed (transaction bytes)
+  uint64_t* kq_empty = bars + 1;   // Q K^T issuer -> producer: Q K^T of an item retired: K and that item's Q buffer may be overwritten
+  uint64_t* q_full = bars + 2;     // [2] producer warp -> Q K^T issuer: block-diagonal Q written
+  uint64_t* v_full = bars + 4;     // [2] TMA -> P V issuer: V tile landed
+  uint64_t* v_empty = bars + 6;    // [2] P V issuer -> producer: P V retired
+  CfmBars bar;
+  bar.s_full = bars + 8;           // [2] Q K^T issuer -> softmax: half of S complete
+  bar.s_empty = bars + 10;         // [2] softmax (16 warps) -> Q K^T issuer: half of S read for the last time
+  // [2] producer warp -> softmax: the item's key mask written.  One barrier per mask buffer (item parity): the producer is
+  // gated by the MMA side, not by the softmax warps, and with a single barrier it can complete the phases of items i and
+  // i+1 before a slow softmax warp has waited for item i -- whose parity test would then never succeed.
+  bar.m_full = bars + 12;
+  bar.p_full = bars + 14;          // [P_RING] softmax (16 warps) -> P V issuer: P chunk written
+  bar.p_empty = bars + 14 + P_RING;      // [P_RING] P V issuer -> softmax: P chunk consumed
+  bar.o_full = bars + 14 + 2 * P_RING;   // [2] P V issuer -> epilogue: O complete
+  bar.o_empty = bars + 16 + 2 * P_RING;  // [2] epilogue (16 warps) -> P V issuer: O read out
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 18 + 2 * P_RING);
+  static_assert(18 + 2 * P_RING < 32, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hp = blockIdx.x & 3, slot = blockIdx.x >> 2, nslots = gridDim.x >> 2;
   const int nW = p.nWh * p.nWw, n_items = p.B * nW;
+  if (threadIdx.x == 0 && p.prof != nullptr) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.prof[(blockIdx.x * 8 + 7) * 32 + 26] = gt;
+    p.prof[(blockIdx.x * 8 + 7) * 32 + 28] = clock64();
+  }
 
   if (warp == SM_WARPS && lane == 0) {
     ptx::prefetch_tensormap(&tmT); ptx::prefetch_tensormap(&tmL1); ptx::prefetch_tensormap(&tmL2);
     ptx::prefetch_tensormap(&tmL3); ptx::prefetch_tensormap(&tmL4);
-    ptx::mbar_init(k_full, 1); ptx::mbar_init(q_full, 1); ptx::mbar_init(kq_empty, 1);
-    ptx::mbar_init(v_full, 1); ptx::mbar_init(v_empty, 1);
-    ptx::mbar_init(s_full, 1); ptx::mbar_init(s_empty, SM_WARPS);
-    for (int i = 0; i < P_RING; ++i) { ptx::mbar_init(&p_full[i], SM_WARPS); ptx::mbar_init(&p_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&o_full[i], 1); ptx::mbar_init(&o_empty[i], SM_WARPS); }
+    ptx::mbar_init(k_full, 1); ptx::mbar_init(kq_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&q_full[i], 1);
+      ptx::mbar_init(&bar.m_full[i], 1);
+      ptx::mbar_init(&bar.s_full[i], 1); ptx::mbar_init(&bar.s_empty[i], SM_WARPS);
+      ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&v_empty[i], 1);
+      ptx::mbar_init(&bar.o_full[i], 1); ptx::mbar_init(&bar.o_empty[i], SM_WARPS);
+    }
+    for (int i = 0; i < P_RING; ++i) { ptx::mbar_init(&bar.p_full[i], SM_WARPS); ptx::mbar_init(&bar.p_empty[i], 1); }
     ptx::fence_barrier_init();
   }
   if (warp == SM_WARPS + 1) {
     ptx::tmem_alloc(tmem_base_smem, 512);
     ptx::tmem_relinquish();
   }
+  // Per-lane constants of the producer's item loop, computed once by ALL threads (one entry each: the divisions would cost
+  // the producer warp ~3000 cycles on its own).  Q piece i (2 x 49 rows x four 16-byte pieces): source offset relative to the
+  // window origin and destination in the block-diagonal tile (rows 0..48 = head 0 in bytes 0..63, rows 64..112 = head 1 in
+  // bytes 64..127).  Key row n of a pooled level sits at (st wi + dy, st wj + dx) of an (f nWh) x (f nWw) map.
+  __shared__ int2 q_tab[2 * 49 * 4];
+  __shared__ int m_tab[NPAD];                                 // dy + 8 | (dx + 8) << 8 | st << 16 | f << 20, or 0: never masked
+  {
+    const int Wa_ = p.nWw * WS + 2 * RING;
+    for (int i = threadIdx.x; i < 2 * 49 * 4; i += CFM_THREADS) {
+      const int pc = i & 3, rq = i >> 2, hl = rq >= 49 ? 1 : 0, q = rq - hl * 49, r = hl * 64 + q;
+      q_tab[i] = make_int2(((q / WS) * Wa_ + q % WS) * CQKV + hl * 32 + pc * 8, r * ROWB + (((hl * 4 + pc) ^ (r & 7)) << 4));
+    }
+    for (int n = threadIdx.x; n < NPAD; n += CFM_THREADS) {
+      int m, kc, st, f;
+      if (n >= R1 && n < R2) { m = n - R1; kc = 5; st = 1; f = 1; }
+      else if (n >= R2 && n < R3) { m = n - R2; kc = 7; st = 1; f = 1; }
+      else if (n >= R3 && n < R4) { m = n - R3; kc = 5; st = 2; f = 2; }
+      else if (n >= R4 && n < REND) { m = n - R4; kc = 3; st = 3; f = 3; }
+      else { m = 0; kc = 1; st = 0; f = 0; }
+      m_tab[n] = f ? ((m / kc - kc / 2 + 8) | ((m % kc - kc / 2 + 8) << 8) | (st << 16) | (f << 20)) : 0;
+    }
+  }
   // K, V, Q tiles start as zeros: rows the TMA boxes never touch (unused key rows, query rows >= 49, the other head's
   // channels of the block-diagonal Q) must stay finite -- they meet P = 0 or are never read back.
-  for (int i = threadIdx.x; i < (2 * L::KV_BYTES + Q_BYTES) / 16; i += CFM_THREADS)
-    reinterpret_cast<uint4*>(sK)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 2 * Q_BYTES / 16; i += CFM_THREADS) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 3 * (NPAD - REND) * (ROWB / 16); i += CFM_THREADS) {      // key rows [277, 288) of K, V, V
+    const int t = i / ((NPAD - REND) * (ROWB / 16)), r = i % ((NPAD - REND) * (ROWB / 16));
+    reinterpret_cast<uint4*>(sK + t * KV_BYTES + REND * ROWB)[r] = make_uint4(0u, 0u, 0u, 0u);
+  }
   if (warp < SM_WARPS) {
     // the head pair's bias slice: a constant table (not produced by the previous kernel), so it is fetched before the
     // programmatic-dependent-launch wait and overlaps the tail of the QKV GEMM
-    const uint4* src = reinterpret_cast<const uint4*>(p.bias_tab + static_cast<int64_t>(hp) * 2 * 49 * L::BPITCH);
-    for (int i = threadIdx.x; i < L::BIAS_BYTES / 16; i += SM_WARPS * 32)
+    const uint4* src = reinterpret_cast<const uint4*>(p.bias_tab + static_cast<int64_t>(hp) * 2 * 49 * BPITCH);
+    for (int i = threadIdx.x; i < BIAS_BYTES / 16; i += SM_WARPS * 32)
       ptx::cp_async16(reinterpret_cast<uint4*>(sBias) + i, src + i);
     ptx::cp_async_commit();
   }
-  ptx::fence_proxy_async();
   ptx::tc_fence_before();
-  __syncthreads();
+  __syncthreads();                                           // zero fill, barrier inits, TMEM address: visible to every warp
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  if (threadIdx.x == 0 && p.prof != nullptr) p.prof[(blockIdx.x * 8 + 7) * 32 + 29] = clock64();
   pdl_sync();
+  if (threadIdx.x == 0 && p.prof != nullptr) p.prof[(blockIdx.x * 8 + 7) * 32 + 30] = clock64();
 
   if (warp == SM_WARPS) {
-    // ===================== producer: TMA K / V boxes, block-diagonal Q =====================
+    // ===================== producer: TMA K / V boxes, block-diagonal Q, key mask =====================
     const int Wa = p.nWw * WS + 2 * RING, Ha = p.nWh * WS + 2 * RING;
-    uint32_t it = 0;
-    for (int item = slot; item < n_items; item += nslots, ++it) {
+    auto boxes = [&](uint8_t* dst, uint64_t* fb, int item, int ct, int cp) {   // ct / cp: channel of K (or V) in qkv / pooled rows
       const int b = item / nW, w = item - b * nW, wi = w / p.nWw, wj = w - wi * p.nWw;
-      if (it > 0) ptx::mbar_wait(kq_empty, (it - 1) & 1u);
-      auto boxes = [&](uint8_t* dst, uint64_t* bar, int ct, int cp) {      // ct / cp: channel of K (or V) in qkv / pooled rows
-        ptx::mbar_arrive_expect_tx(bar, L::TX_BYTES);
-        ptx::tma_load_4d(dst, &tmT, bar, ct, WS * wj, WS * wi, b);
-        ptx::tma_load_4d(dst + L::R1 * ROWB, &tmL1, bar, cp, wj - 2, wi - 2, b);
-        ptx::tma_load_4d(dst + L::R2 * ROWB, &tmL2, bar, cp, wj - 3, wi - 3, b);
-        ptx::tma_load_4d(dst + L::R3 * ROWB, &tmL3, bar, cp, 2 * wj - 2, 2 * wi - 2, b);
-        ptx::tma_load_4d(dst + L::R4 * ROWB, &tmL4, bar, cp, 3 * wj - 1, 3 * wi - 1, b);
-      };
-      if (lane == 0) boxes(sK, k_full, 256 + hp * CPAIR, hp * CPAIR);
-      // Q: rows 0..48 = head 0 (bytes 0..63 of the row), rows 64..112 = head 1 (bytes 64..127); 16-byte pieces
-      for (int i = lane; i < 2 * 49 * 4; i += 32) {
-        const int pc = i & 3, rq = i >> 2, hl = rq >= 49 ? 1 : 0, q = rq - hl * 49;
-        const int r = hl * 64 + q;
-        const __half* src = p.qkv_a + ((static_cast<int64_t>(b) * Ha + WS * wi + RING + q / WS) * Wa + WS * wj + RING + q % WS) * CQKV +
-                            hp * CPAIR + hl * 32 + pc * 8;
-        ptx::cp_async16(sQ + r * ROWB + (((hl * 4 + pc) ^ (r & 7)) << 4), src);
+      ptx::mbar_arrive_expect_tx(fb, TX_BYTES);
+      ptx::tma_load_4d(dst, &tmT, fb, ct, WS * wj, WS * wi, b);
+      ptx::tma_load_4d(dst + R1 * ROWB, &tmL1, fb, cp, wj - 2, wi - 2, b);
+      ptx::tma_load_4d(dst + R2 * ROWB, &tmL2, fb, cp, wj - 3, wi - 3, b);
+      ptx::tma_load_4d(dst + R3 * ROWB, &tmL3, fb, cp, 2 * wj - 2, 2 * wi - 2, b);
+      ptx::tma_load_4d(dst + R4 * ROWB, &tmL4, fb, cp, 3 * wj - 1, 3 * wi - 1, b);
+    };
+    auto dump_tile = [&](const uint8_t* tile, int item, int which) {           // test hook: an assembled tile, de-swizzled
+      __half* d = p.dump + ((static_cast<int64_t>(hp) * n_items + item) * 2 + which) * NPAD * CPAIR;
+      for (int i = lane; i < NPAD * 8; i += 32) {
+        const int n = i >> 3, pc = i & 7;
+        *reinterpret_cast<uint4*>(d + n * CPAIR + pc * 8) = *reinterpret_cast<const uint4*>(tile + n * ROWB + ((pc ^ (n & 7)) << 4));
       }
+    };
+    ptx::fence_proxy_async();                                // the zero fill (generic proxy) is ordered before the first TMA write
+    // per-lane constants of the item loop (this warp shares its scheduler with four softmax warps: keep it lean)
+    constexpr int QP = (2 * 49 * 4 + 31) / 32, MP = NPAD / 32;
+    int q_src[QP], q_dst[QP], m_par[MP];
+#pragma unroll
+    for (int j = 0; j < QP; ++j) {
+      const int i = lane + 32 * j;
+      const int2 e = q_tab[i < 2 * 49 * 4 ? i : 0];
+      q_src[j] = i < 2 * 49 * 4 ? e.x : -1;
+      q_dst[j] = e.y;
+    }
+#pragma unroll
+    for (int j = 0; j < MP; ++j) m_par[j] = m_tab[lane + 32 * j];
+    // Q of an item: 13 cp.async per lane into the block-diagonal tile `buf`; published on q_full[buf] by finish_q
+    auto issue_q = [&](int item, uint32_t buf) {
+      const int b = item / nW, w = item - b * nW, wi = w / p.nWw, wj = w - wi * p.nWw;
+      const __half* qbase = p.qkv_a + ((static_cast<int64_t>(b) * Ha + WS * wi + RING) * Wa + WS * wj + RING) * CQKV + hp * CPAIR;
+#pragma unroll
+      for (int j = 0; j < QP; ++j)
+        if (q_src[j] >= 0) ptx::cp_async16(sQ + buf * Q_BYTES + q_dst[j], qbase + q_src[j]);
       ptx::cp_async_commit();
+    };
+    auto finish_q = [&](uint32_t buf) {
       ptx::cp_async_wait_all();
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(q_full);
-      if (p.dump != nullptr) {                               // test hook: the assembled K tile, de-swizzled
-        ptx::mbar_wait(k_full, it & 1u);
-        __half* d = p.dump + (static_cast<int64_t>(hp) * n_items + item) * 2 * L::NPAD * CPAIR;
-        for (int i = lane; i < L::NPAD * 8; i += 32) {
-          const int n = i >> 3, pc = i & 7;
-          *reinterpret_cast<uint4*>(d + n * CPAIR + pc * 8) = *reinterpret_cast<const uint4*>(sK + n * ROWB + ((pc ^ (n & 7)) << 4));
-        }
+      if (lane == 0) ptx::mbar_arrive(&q_full[buf]);
+    };
+    if (slot < n_items) {                                    // first item: K and Q first (Q K^T needs them), V behind
+      if (lane == 0) boxes(sK, k_full, slot, 256 + hp * CPAIR, hp * CPAIR);
+      issue_q(slot, 0);
+      if (lane == 0) boxes(sV, &v_full[0], slot, 512 + hp * CPAIR, 256 + hp * CPAIR);
+      finish_q(0);
+    }
+    uint32_t it = 0;
+    for (int item = slot; item < n_items; item += nslots, ++it) {
+      const int b = item / nW, w = item - b * nW, wi = w / p.nWw, wj = w - wi * p.nWw;
+      const int next = item + nslots;
+      // Q K^T of item it-1 has retired: K and the Q buffer of item it-1 (= that of item it+1) are free
+      if (it > 0) {
+        ptx::mbar_wait(kq_empty, (it - 1) & 1u);
+        if (lane == 0) { CFM_PROF(0); boxes(sK, k_full, item, 256 + hp * CPAIR, hp * CPAIR); }
       }
-      if (it > 0) ptx::mbar_wait(v_empty, (it - 1) & 1u);
-      if (lane == 0) boxes(sV, v_full, 512 + hp * CPAIR, 256 + hp * CPAIR);
+      if (next < n_items) issue_q(next, (it + 1) & 1u);      // Q a whole item ahead; its latency hides behind the mask below
+      // the item's key mask; its buffer was last read for item it-2, whose reads precede kq_empty(it-1)
+      float* mask = sMask + (it & 1u) * (NPAD + 4);
+      if (lane < 3) reinterpret_cast<int*>(mask + NPAD)[lane] = lane == 0 ? b : (lane == 1 ? wi : wj);   // the softmax warps do not redo the divisions
+#pragma unroll
+      for (int j = 0; j < MP; ++j) {
+        const int mp = m_par[j], st = (mp >> 16) & 15, f = mp >> 20;
+        const int y = st * wi + (mp & 255) - 8, x = st * wj + ((mp >> 8) & 255) - 8;
+        mask[lane + 32 * j] = (f == 0 || (y >= 0 && y < f * p.nWh && x >= 0 && x < f * p.nWw)) ? 0.f : -INFINITY;
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar.m_full[it & 1u]);
+      if (next < n_items) { finish_q((it + 1) & 1u); if (lane == 0) CFM_PROF(1); }
       if (p.dump != nullptr) {
-        ptx::mbar_wait(v_full, it & 1u);
-        __half* d = p.dump + ((static_cast<int64_t>(hp) * n_items + item) * 2 + 1) * L::NPAD * CPAIR;
-        for (int i = lane; i < L::NPAD * 8; i += 32) {
-          const int n = i >> 3, pc = i & 7;
-          *reinterpret_cast<uint4*>(d + n * CPAIR + pc * 8) = *reinterpret_cast<const uint4*>(sV + n * ROWB + ((pc ^ (n & 7)) << 4));
-        }
+        ptx::mbar_wait(k_full, it & 1u);
+        dump_tile(sK, item, 0);
+        ptx::mbar_wait(&v_full[it & 1u], (it >> 1) & 1u);
+        dump_tile(sV + (it & 1u) * KV_BYTES, item, 1);
+        __syncwarp();
+      }
+      // V of the NEXT item, a whole item ahead of its first use
+      if (next < n_items) {
+        const uint32_t nb = (it + 1) & 1u;
+        if (it >= 1) ptx::mbar_wait(&v_empty[nb], ((it - 1) >> 1) & 1u);
+        if (lane == 0) { CFM_PROF(2); boxes(sV + nb * KV_BYTES, &v_full[nb], next, 512 + hp * CPAIR, 256 + hp * CPAIR); }
       }
     }
   } else if (warp == SM_WARPS + 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer (one thread) =====================
-      constexpr int NH2 = L::NPAD / 2;
-      constexpr uint32_t idesc_qk = ptx::make_idesc_f16(128, NH2);                       // A, B K-major
-      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(128, CPAIR) | (1u << 16);         // B (= V) MN-major
-      const uint64_t dq = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ));
-      const uint64_t dk = ptx::make_smem_desc_sw128(ptx::smem_u32(sK));
-      const uint32_t my_items = slot < n_items ? (n_items - slot + nslots - 1) / nslots : 0u;
-      for (uint32_t it = 0; it < my_items; ++it) {
-        ptx::mbar_wait(k_full, it & 1u);
-        ptx::mbar_wait(q_full, it & 1u);
-        if (it > 0) ptx::mbar_wait(s_empty, (it - 1) & 1u);
-        ptx::tc_fence_after();
+    // ===================== P V issuer =====================
+    // The two MMA roles are separate warps on separate schedulers: each is a short, latency-bound instruction stream that
+    // competes with four busy softmax warps for issue slots; as ONE warp the issue of P V fell ~1300 cycles behind the
+    // softmax by the end of every item.  In both, the whole warp walks the loop and waits on the barriers and ONE elected
+    // lane issues the tcgen05 instructions (entering the role with `if (lane == 0)` makes every descriptor a per-thread
+    // value: each UTCHMMA is then wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop of ~15 dependent instructions).
+    constexpr uint32_t idesc_pv = ptx::make_idesc_f16(128, CPAIR) | (1u << 16);         // B (= V) MN-major
+    const uint64_t dv0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sV));
+    const uint32_t my_items = slot < n_items ? (n_items - slot + nslots - 1) / nslots : 0u;
+    if (lane == 0) ptx::fence_proxy_async();                 // the zero fill of the pad rows -> async proxy (tensor core reads)
+    __syncwarp();
+    for (uint32_t it = 0; it < my_items; ++it) {
+      const uint32_t ob = it & 1u, vb = it & 1u;
+      const uint32_t tmem_o = tmem_base + TMEM_O + ob * 64;
+      uint64_t dv = dv0 + static_cast<uint64_t>(vb * (KV_BYTES / 16));
+      uint32_t gc = it * NCH;
 #pragma unroll
-        for (int half = 0; half < 2; ++half)
+      for (int c = 0; c < NCH; ++c, ++gc) {
+        const uint32_t ps = gc % P_RING;
+        ptx::mbar_wait(&bar.p_full[ps], (gc / P_RING) & 1u);
+        if (c == 0) {
+          if (lane == 0) CFM_PROF(6);
+          ptx::mbar_wait(&v_full[vb], (it >> 1) & 1u);
+          if (it >= 2) ptx::mbar_wait(&bar.o_empty[ob], ((it - 2) >> 1) & 1u);
+          if (lane == 0) CFM_PROF(7);
+        }
+        ptx::tc_fence_after();
+        const uint32_t tp = tmem_base + TMEM_P + ps * P_COLS;
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < ((c * 64 + 64 <= NPAD) ? 4 : 2); ++k)
+            // 16 keys per MMA: A (P in TMEM) advances 8 cells, B (MN-major V) advances 16 key rows
+            ptx::umma_f16_ts(tmem_o, tp + 8u * k, dv + static_cast<uint64_t>(k * (16 * ROWB / 16)), idesc_pv, (c | k) != 0 ? 1u : 0u);
+          ptx::umma_commit(&bar.p_empty[ps]);
+          if (c == NCH - 1) {
+            ptx::umma_commit(&bar.o_full[ob]);
+            ptx::umma_commit(&v_empty[vb]);
+          }
+        }
+        __syncwarp();
+        dv += 4 * (16 * ROWB / 16);
+      }
+      if (lane == 0) CFM_PROF(13);
+    }
+  } else if (warp == SM_WARPS + 2) {
+    // ===================== Q K^T issuer =====================
+    // S is produced and released in two halves: columns [0,128) of item i+1 are written as soon as every softmax warp has
+    // read them for the last time in its second pass over item i, columns [128,288) after the last read of S.  The softmax
+    // warps therefore find the next item's scores ready when they get there.
+    constexpr uint32_t idesc_qa = ptx::make_idesc_f16(128, N_A), idesc_qb = ptx::make_idesc_f16(128, N_B);   // A, B K-major
+    const uint64_t dq0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ));
+    const uint64_t dk = ptx::make_smem_desc_sw128(ptx::smem_u32(sK));
+    const uint32_t my_items = slot < n_items ? (n_items - slot + nslots - 1) / nslots : 0u;
+    if (lane == 0) ptx::fence_proxy_async();                 // the zero fill of the pad rows -> async proxy (tensor core reads)
+    __syncwarp();
+    for (uint32_t it = 0; it < my_items; ++it) {
+      const uint64_t dq = dq0 + static_cast<uint64_t>((it & 1u) * (Q_BYTES / 16));
+      ptx::mbar_wait(k_full, it & 1u);
+      if (lane == 0) CFM_PROF(3);
+      ptx::mbar_wait(&q_full[it & 1u], (it >> 1) & 1u);
+      if (lane == 0) CFM_PROF(4);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (it > 0) ptx::mbar_wait(&bar.s_empty[half], (it - 1) & 1u);
+        ptx::tc_fence_after();
+        if (half == 1 && lane == 0) CFM_PROF(5);
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::umma_f16(tmem_base + half * NH2, dq + 2u * k, dk + static_cast<uint64_t>(half * NH2 * (ROWB / 16)) + 2u * k,
-                          idesc_qk, k != 0 ? 1u : 0u);
-        ptx::umma_commit(s_full);
-        ptx::umma_commit(kq_empty);
-        const uint32_t ob = it & 1u;
-        const uint32_t tmem_o = tmem_base + L::TMEM_O + ob * 64;
-#pragma unroll 1
-        for (int c = 0; c < L::NCH; ++c) {
-          const uint32_t gc = it * L::NCH + c, ps = gc % P_RING;
-          ptx::mbar_wait(&p_full[ps], (gc / P_RING) & 1u);
-          if (c == 0) {
-            ptx::mbar_wait(v_full, it & 1u);
-            if (it >= 2) ptx::mbar_wait(&o_empty[ob], ((it - 2) >> 1) & 1u);
-          }
-          ptx::tc_fence_after();
-          const uint64_t dp = ptx::make_smem_desc_sw128(ptx::smem_u32(sP + ps * P_CHUNK_BYTES));
-          const int ksteps = (c * 64 + 64 <= L::NPAD) ? 4 : 2;
-          for (int k = 0; k < ksteps; ++k) {
-            // 16 keys per MMA: A advances 32 bytes inside the swizzled row, B (MN-major V) advances 16 key rows
-            const uint64_t dv = ptx::make_smem_desc_sw128(ptx::smem_u32(sV + (c * 64 + k * 16) * ROWB));
-            ptx::umma_f16(tmem_o, dp + 2u * k, dv, idesc_pv, (c | k) != 0 ? 1u : 0u);
-          }
-          ptx::umma_commit(&p_empty[ps]);
+            ptx::umma_f16(tmem_base + half * N_A, dq + 2u * k, dk + static_cast<uint64_t>(half * N_A * (ROWB / 16)) + 2u * k,
+                          half ? idesc_qb : idesc_qa, k != 0 ? 1u : 0u);
+          ptx::umma_commit(&bar.s_full[half]);
+          if (half == 1) ptx::umma_commit(kq_empty);
         }
-        ptx::umma_commit(&o_full[ob]);
-        ptx::umma_commit(v_empty);
+        __syncwarp();
       }
     }
   } else {
     ptx::cp_async_wait_all();                                // bias slice (this thread's pieces)
-    asm volatile("bar.sync 5, 256;" ::: "memory");           // ... and everybody else's
-    if ((warp >> 2) == 0)
-      softmax_role<AL, 0>(p, sP, sBias, sMask, sX, s_full, s_empty, p_full, p_empty, o_full, o_empty, tmem_base, hp, slot, nslots);
-    else
-      softmax_role<AL, 1>(p, sP, sBias, sMask, sX, s_full, s_empty, p_full, p_empty, o_full, o_empty, tmem_base, hp, slot, nslots);
+    asm volatile("bar.sync 5, 512;" ::: "memory");           // ... and everybody else's
+    softmax_role(p, sBias, sMask, sX, bar, tmem_base, hp, slot, nslots);
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0 && p.prof != nullptr) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.prof[(blockIdx.x * 8 + 7) * 32 + 27] = gt;
+    p.prof[(blockIdx.x * 8 + 7) * 32 + 31] = clock64();
+  }
   if (warp == SM_WARPS + 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-bool cfm_aligned_layout() {
-  static const bool on = [] { const char* e = getenv("CFFM_CFM_ALIGNED"); return e && e[0] == '1'; }();
-  return on;
-}
-
-template <bool AL>
 int launch_cfm(const CUtensorMap* tm, const CfmParams& p, cudaStream_t st) {
-  using L = Lay<AL>;
   static cudaError_t attr_err =
-      cudaFuncSetAttribute(cfm_attention_tc_kernel<AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM);
-  CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute(%d bytes): %s", L::SMEM, cudaGetErrorString(attr_err));
+      cudaFuncSetAttribute(cfm_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CFM_SMEM);
+  CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute(%d bytes): %s", CFM_SMEM, cudaGetErrorString(attr_err));
   // persistent CTAs, each bound to one head pair (its bias slice stays in shared memory) and walking over (clip, window) items
   const int n_items = p.B * p.nWh * p.nWw;
   int nslots = num_sms() / 4;
   if (nslots > n_items) nslots = n_items;
   if (nslots < 1) nslots = 1;
-  launch_k(cfm_attention_tc_kernel<AL>, nslots * 4, CFM_THREADS, L::SMEM, st, tm[0], tm[1], tm[2], tm[3], tm[4], p);
+  launch_k(cfm_attention_tc_kernel, nslots * 4, CFM_THREADS, CFM_SMEM, st, tm[0], tm[1], tm[2], tm[3], tm[4], p);
   return launch_status("cfm_attention_tc_kernel");
 }
 
 int cfm_run(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void* out, void* dump, int B, int H, int W, int C,
-            int heads, float scale, void* stream) {
+            int heads, float scale, void* stream, long long* prof = nullptr) {
   CFFM_REQUIRE(qkv_a && kv_pooled && bias_tab && out, CFFM_E_BADARG, "cfm_attention: null pointer");
   CFFM_REQUIRE(B > 0 && H > 0 && W > 0 && scale > 0.f, CFFM_E_BADARG, "cfm_attention: non-positive size or scale");
   CFFM_REQUIRE(C == 256 && heads == 8, CFFM_E_UNSUPPORTED,
@@ -464,10 +601,11 @@ int cfm_run(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void
   p.bias_tab = static_cast<const __half*>(bias_tab);
   p.out = static_cast<__half*>(out);
   p.dump = static_cast<__half*>(dump);
+  p.prof = prof;
   p.B = B; p.H = H; p.W = W; p.nWh = nWh; p.nWw = nWw;
   p.scale_log2e = scale * LOG2E;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return cfm_aligned_layout() ? launch_cfm<true>(tm, p, st) : launch_cfm<false>(tm, p, st);
+  return launch_cfm(tm, p, st);
 }
 
 }  // namespace
@@ -487,14 +625,13 @@ extern "C" int cffm_cfm_attention_dump(const void* qkv_a, const void* kv_pooled,
 extern "C" int cffm_cfm_layout(int32_t* out8) {
   using namespace cffm;
   CFFM_REQUIRE(out8 != nullptr, CFFM_E_BADARG, "cfm_layout: null pointer");
-  const bool al = cfm_aligned_layout();
-  out8[0] = 0;
-  out8[1] = al ? Lay<true>::R1 : Lay<false>::R1;
-  out8[2] = al ? Lay<true>::R2 : Lay<false>::R2;
-  out8[3] = al ? Lay<true>::R3 : Lay<false>::R3;
-  out8[4] = al ? Lay<true>::R4 : Lay<false>::R4;
-  out8[5] = al ? Lay<true>::NPAD : Lay<false>::NPAD;
-  out8[6] = al ? Lay<true>::BPITCH : Lay<false>::BPITCH;
+  out8[0] = 0; out8[1] = R1; out8[2] = R2; out8[3] = R3; out8[4] = R4; out8[5] = NPAD; out8[6] = BPITCH;
   out8[7] = RING;
   return CFFM_OK;
+}
+
+/* Bring-up hook (not in the header): SM-clock stamps of the pipeline events of the first 8 items of every CTA. */
+extern "C" int cffm_cfm_attention_prof(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void* out, void* prof,
+                                       int B, int H, int W, int C, int heads, float scale, void* stream) {
+  return cffm::cfm_run(qkv_a, kv_pooled, bias_tab, out, nullptr, B, H, W, C, heads, scale, stream, static_cast<long long*>(prof));
 }

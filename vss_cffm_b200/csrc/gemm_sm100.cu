@@ -138,48 +138,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_base_smem;
   pdl_sync();                                                  // prologue above overlaps the previous kernel
 
+  // Producer and MMA roles: the WHOLE warp walks the loop and waits on the barriers, one ELECTED lane issues the TMA /
+  // tcgen05 instructions.  (Entering a role with `if (lane == 0)` makes every descriptor a per-thread value, and ptxas then
+  // wraps each UTMALDG / UTCHMMA / UTCBAR in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop: ~15 dependent instructions per
+  // MMA, which made the issuing thread slower than the tensor core for the K = 64 tiles.)
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      uint32_t g = 0;                                          // k-blocks issued so far (all tiles)
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int split = t % ep.splits, tt = t / ep.splits;
-        const int m0 = (tt / n_tiles_n) * BLOCK_M, n0 = (tt % n_tiles_n) * BN;
-        const int kb0 = split * ep.kb_per, kb1 = min(num_kb, kb0 + ep.kb_per);
-        for (int kb = kb0; kb < kb1; ++kb, ++g) {
-          const uint32_t s = g % C::STAGES, ph = (g / C::STAGES) & 1u;
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1u);              // slot free (passes on the first round)
+    // ===================== TMA producer =====================
+    uint32_t g = 0;                                            // k-blocks issued so far (all tiles)
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int split = t % ep.splits, tt = t / ep.splits;
+      const int m0 = (tt / n_tiles_n) * BLOCK_M, n0 = (tt % n_tiles_n) * BN;
+      const int kb0 = split * ep.kb_per, kb1 = min(num_kb, kb0 + ep.kb_per);
+      for (int kb = kb0; kb < kb1; ++kb, ++g) {
+        const uint32_t s = g % C::STAGES, ph = (g / C::STAGES) & 1u;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);                // slot free (passes on the first round)
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
           ptx::tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BLOCK_K, m0);
           ptx::tma_load_2d(sW + s * C::W_STAGE_BYTES, &tmW, &full_bar[s], kb * BLOCK_K, n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer (one thread) =====================
-      constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BN);
-      uint32_t g = 0, it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
-        ptx::mbar_wait(&tempty_bar[acc], aph ^ 1u);            // epilogue drained this accumulator stage
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BN);
+    uint32_t g = 0, it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+      ptx::mbar_wait(&tempty_bar[acc], aph ^ 1u);              // epilogue drained this accumulator stage
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      const int kb0 = (t % ep.splits) * ep.kb_per, kb1 = min(num_kb, kb0 + ep.kb_per);
+      for (int kb = kb0; kb < kb1; ++kb, ++g) {
+        const uint32_t s = g % C::STAGES, ph = (g / C::STAGES) & 1u;
+        ptx::mbar_wait(&full_bar[s], ph);                      // TMA bytes have landed
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        const int kb0 = (t % ep.splits) * ep.kb_per, kb1 = min(num_kb, kb0 + ep.kb_per);
-        for (int kb = kb0; kb < kb1; ++kb, ++g) {
-          const uint32_t s = g % C::STAGES, ph = (g / C::STAGES) & 1u;
-          ptx::mbar_wait(&full_bar[s], ph);                    // TMA bytes have landed
-          ptx::tc_fence_after();
-          const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(sA + s * A_STAGE_BYTES));
-          const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(sW + s * C::W_STAGE_BYTES));
+        const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(sA + s * A_STAGE_BYTES));
+        const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(sW + s * C::W_STAGE_BYTES));
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 halves = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
             ptx::umma_f16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[s]);                     // frees the smem slot when the MMAs retire
+          if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[acc]);     // accumulator complete
         }
-        ptx::umma_commit(&tfull_bar[acc]);                     // accumulator complete
+        __syncwarp();
       }
     }
   } else {

@@ -87,59 +87,71 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   // columns are dead once P chunk 0 has been produced, which is exactly when the first PV MMA is issued.  The MMA
   // warp issues Q K^T of item i+1 (other buffer) before P V of item i, so the tensor pipe works on the next tile
   // while the softmax warps are busy with the current one.
+  // Producer and MMA roles: the whole warp walks the loop and waits on the barriers, one ELECTED lane issues the TMA /
+  // tcgen05 instructions (with `if (lane == 0)` ptxas wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT + R2UR.BROADCAST
+  // + BRA.U.ANY loop, ~15 dependent instructions each).
   if (warp == SM_WARPS) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int qt = item % qtiles, bh = item / qtiles, h = bh % heads, b = bh / heads;
-        const uint32_t buf = it & 1u, bph = (it >> 1) & 1u;
-        ptx::mbar_wait(qk_empty, (it & 1u) ^ 1u);
+    // ===================== TMA producer =====================
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int qt = item % qtiles, bh = item / qtiles, h = bh % heads, b = bh / heads;
+      const uint32_t buf = it & 1u, bph = (it >> 1) & 1u;
+      ptx::mbar_wait(qk_empty, (it & 1u) ^ 1u);
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(qk_full, Q_BYTES + KV_BYTES);
         ptx::tma_load_2d(sQ, &tmQ, qk_full, h * D, b * Nq + qt * QT);
         ptx::tma_load_2d(sK, &tmK, qk_full, h * D, b * Nkv);
-        ptx::mbar_wait(&v_empty[buf], bph ^ 1u);
+      }
+      __syncwarp();
+      ptx::mbar_wait(&v_empty[buf], bph ^ 1u);
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&v_full[buf], KV_BYTES);
         ptx::tma_load_2d(sV + buf * KV_BYTES, &tmV, &v_full[buf], h * D, b * Nkv);
       }
+      __syncwarp();
     }
   } else if (warp == SM_WARPS + 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer (one thread) =====================
-      constexpr uint32_t idesc_qk = ptx::make_idesc_f16(QT, KV_MAX);                    // A, B K-major
-      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(QT, D) | (1u << 16);            // B (= V) MN-major
-      const uint64_t dq = desc_sw128(ptx::smem_u32(sQ)), dk = desc_sw128(ptx::smem_u32(sK));
-      auto issue_qk = [&](uint32_t j) {                        // S[j & 1] = Q K^T of the CTA's j-th item
-        ptx::mbar_wait(qk_full, j & 1u);
-        if (j >= 2) ptx::mbar_wait(&o_empty[j & 1u], ((j - 2) >> 1) & 1u);   // O of item j-2 (same buffer) was read
-        ptx::tc_fence_after();
-        const uint32_t tmem_s = tmem_base + (j & 1u) * KV_MAX;
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = ptx::make_idesc_f16(QT, KV_MAX);                    // A, B K-major
+    constexpr uint32_t idesc_pv = ptx::make_idesc_f16(QT, D) | (1u << 16);            // B (= V) MN-major
+    const uint64_t dq = desc_sw128(ptx::smem_u32(sQ)), dk = desc_sw128(ptx::smem_u32(sK));
+    auto issue_qk = [&](uint32_t j) {                          // S[j & 1] = Q K^T of the CTA's j-th item
+      ptx::mbar_wait(qk_full, j & 1u);
+      if (j >= 2) ptx::mbar_wait(&o_empty[j & 1u], ((j - 2) >> 1) & 1u);   // O of item j-2 (same buffer) was read
+      ptx::tc_fence_after();
+      const uint32_t tmem_s = tmem_base + (j & 1u) * KV_MAX;
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) ptx::umma_f16(tmem_s, dq + 2u * k, dk + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
         ptx::umma_commit(&s_full[j & 1u]);
         ptx::umma_commit(qk_empty);
-      };
-      const uint32_t my_items = blockIdx.x < static_cast<uint32_t>(n_items)
-                                    ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
-      if (my_items > 0) issue_qk(0);
-      for (uint32_t it = 0; it < my_items; ++it) {
-        const uint32_t buf = it & 1u, bph = (it >> 1) & 1u;
-        if (it + 1 < my_items) issue_qk(it + 1);               // next tile's scores while this tile's softmax runs
-        ptx::mbar_wait(&v_full[buf], bph);
-        const uint32_t tmem_o = tmem_base + buf * KV_MAX;
-        for (int c = 0; c < 4; ++c) {
-          ptx::mbar_wait(&p_full[c], it & 1u);
-          ptx::tc_fence_after();
-          const uint64_t dp = desc_sw128(ptx::smem_u32(sP + c * P_CHUNK_BYTES));
+      }
+      __syncwarp();
+    };
+    const uint32_t my_items = blockIdx.x < static_cast<uint32_t>(n_items)
+                                  ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    if (my_items > 0) issue_qk(0);
+    for (uint32_t it = 0; it < my_items; ++it) {
+      const uint32_t buf = it & 1u, bph = (it >> 1) & 1u;
+      if (it + 1 < my_items) issue_qk(it + 1);                 // next tile's scores while this tile's softmax runs
+      ptx::mbar_wait(&v_full[buf], bph);
+      const uint32_t tmem_o = tmem_base + buf * KV_MAX;
+      for (int c = 0; c < 4; ++c) {
+        ptx::mbar_wait(&p_full[c], it & 1u);
+        ptx::tc_fence_after();
+        const uint64_t dp = desc_sw128(ptx::smem_u32(sP + c * P_CHUNK_BYTES));
+        // 16 keys per MMA: A advances 32 bytes inside the swizzled row, B (MN-major V) advances 16 key rows
+        const uint64_t dv = desc_sw128(ptx::smem_u32(sV + buf * KV_BYTES + c * 64 * (D * 2)));
+        if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // 16 keys per MMA: A advances 32 bytes inside the swizzled row, B (MN-major V) advances 16 key rows
-            const uint64_t dv = desc_sw128(ptx::smem_u32(sV + buf * KV_BYTES + (c * 64 + k * 16) * (D * 2)));
-            ptx::umma_f16(tmem_o, dp + 2u * k, dv, idesc_pv, (c | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_f16(tmem_o, dp + 2u * k, dv + static_cast<uint64_t>(k * (16 * D * 2 / 16)), idesc_pv, (c | k) != 0 ? 1u : 0u);
+          if (c == 3) {
+            ptx::umma_commit(&o_full[buf]);
+            ptx::umma_commit(&v_empty[buf]);
           }
         }
-        ptx::umma_commit(&o_full[buf]);
-        ptx::umma_commit(&v_empty[buf]);
+        __syncwarp();
       }
     }
   } else {
