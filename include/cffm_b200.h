@@ -203,6 +203,20 @@ int cffm_cffa_pool_level(const void* xn, int n_frames, int level, int H, int W, 
 int cffm_cfm_attention(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void* out, int B,
                        int H, int W, int C, int heads, float scale, void* stream);
 
+/* Same kernel with the pooled K/V addressed level by level (frame-sharded multi-GPU runs read the
+ * all-gathered reference-frame buffer in place, no per-clip copies):
+ *   kv_tgt       pooled target level fp16 [B, nW, 2C], clip stride tgt_stride (elements)
+ *   kv_ref{k}    base of the level maps of reference role k (nW / 4 nW / 9 nW tokens x 2C per map); the map of
+ *                slot s contributed by rank r starts s * slot_stride{k} + r * rank_stride elements further
+ *   n_slots{k}   slots per rank of role k; n_ranks = ranks behind the buffer
+ *   ref_slot     DEVICE table int32 [B, 3, 2]: (slot, rank) of reference frame k of clip b; NULL = (b, 0) */
+int cffm_cfm_attention_slots(const void* qkv_a, const void* kv_tgt, int64_t tgt_stride, const void* kv_ref0,
+                             const void* kv_ref1, const void* kv_ref2, int64_t slot_stride0,
+                             int64_t slot_stride1, int64_t slot_stride2, int n_slots0, int n_slots1,
+                             int n_slots2, int64_t rank_stride, int n_ranks, const int32_t* ref_slot,
+                             const void* bias_tab, void* out, int B, int H, int W, int C, int heads, float scale,
+                             void* stream);
+
 /* Test entry: the same kernel, additionally writing the assembled K and V tiles of every work item
  * (head pair hp, clip b, window w) to dump fp16 [4, B*nW, 2, NPAD, 64] (K then V; row order =
  * cffm_cfm_layout) so that the TMA assembling can be compared bit for bit with the reference's

@@ -89,3 +89,26 @@ def test_kv_all_gather_world2_gloo(Bg):
         msgs.append(errs.get())
     assert not msgs, msgs
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+
+
+@pytest.mark.parametrize("Bg,G", [(16, 8), (4, 2), (2, 2), (3, 2), (2, 8)])
+def test_role_packing_indexes_every_reference_frame(Bg, G):
+    """The packed per-role layout of the exchange: (index, rank) of every reference frame is unique inside its role and below
+    the role's slot count; offsets tile the buffer without overlap."""
+    plan = FrameShardPlan(Bg, 4, G)
+    nW = 81
+    off, total = plan.role_offsets(nW)
+    assert off[0] == 0 and total == sum(plan.role_slots[k] * ROLE_TOKENS[k] * nW for k in range(3))
+    for k in range(3):
+        seen = set()
+        for b in range(Bg):
+            idx, rank = plan.role_index(b, k)
+            assert rank == plan.owner(b, k) and 0 <= idx < plan.role_slots[k] and (idx, rank) not in seen
+            seen.add((idx, rank))
+        assert plan.role_slots[k] == max(1, max(c[k] for c in plan.role_count))
+    # the frames of a rank are frame-major, so its role-k frames are contiguous and in role_index order
+    for r in range(G):
+        pos = {0: 0, 1: 0, 2: 0}
+        for (b, t) in plan.refs[r]:
+            assert plan.role_index(b, t) == (pos[t], r)
+            pos[t] += 1

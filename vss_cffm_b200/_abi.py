@@ -52,6 +52,7 @@ SIGNATURES = {
     "cffm_kmeans_update": ([vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp], i32),
     "cffm_transpose_f16": ([vp, i32, i32, vp, i32, vp], i32),
     "cffm_cfm_attention": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),
+    "cffm_cfm_attention_slots": ([vp, vp, i64, vp, vp, vp, i64, i64, i64, i32, i32, i32, i64, i32, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),
     "cffm_cfm_attention_dump": ([vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp], i32),
     "cffm_cfm_layout": ([vp], i32),
     "cffm_resize_nhwc_to_nchw": ([vp, i32, i64, vp, i32, i32, i32, i32, i32, i32, vp], i32),

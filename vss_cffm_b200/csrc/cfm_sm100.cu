@@ -70,6 +70,7 @@ struct CfmParams {
   __half* out;              // [B, H, W, 256]
   __half* dump;             // test hook: [4 head pairs, B nW items, 2, NPAD, 64] assembled K and V tiles (or null)
   long long* prof;          // bring-up hook: per CTA / item / event SM clock stamps [grid, 8, 32] (or null)
+  const int32_t* ref_slot;  // [B, 3, 2] (slot, rank) = 4th and 5th coordinate of the level map of reference frame k of clip b, or null: (b, 0)
   int B, H, W, nWh, nWw;
   float scale_log2e;
 };
@@ -379,12 +380,18 @@ cfm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_co
     const int Wa = p.nWw * WS + 2 * RING, Ha = p.nWh * WS + 2 * RING;
     auto boxes = [&](uint8_t* dst, uint64_t* fb, int item, int ct, int cp) {   // ct / cp: channel of K (or V) in qkv / pooled rows
       const int b = item / nW, w = item - b * nW, wi = w / p.nWw, wj = w - wi * p.nWw;
+      // where the three reference frames of this clip live (frame-sharded runs read the all-gathered buffer in place)
+      int sl[3] = {b, b, b}, rk[3] = {0, 0, 0};
+      if (p.ref_slot != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { sl[k] = p.ref_slot[6 * b + 2 * k]; rk[k] = p.ref_slot[6 * b + 2 * k + 1]; }
+      }
       ptx::mbar_arrive_expect_tx(fb, TX_BYTES);
       ptx::tma_load_4d(dst, &tmT, fb, ct, WS * wj, WS * wi, b);
       ptx::tma_load_4d(dst + R1 * ROWB, &tmL1, fb, cp, wj - 2, wi - 2, b);
-      ptx::tma_load_4d(dst + R2 * ROWB, &tmL2, fb, cp, wj - 3, wi - 3, b);
-      ptx::tma_load_4d(dst + R3 * ROWB, &tmL3, fb, cp, 2 * wj - 2, 2 * wi - 2, b);
-      ptx::tma_load_4d(dst + R4 * ROWB, &tmL4, fb, cp, 3 * wj - 1, 3 * wi - 1, b);
+      ptx::tma_load_5d(dst + R2 * ROWB, &tmL2, fb, cp, wj - 3, wi - 3, sl[0], rk[0]);
+      ptx::tma_load_5d(dst + R3 * ROWB, &tmL3, fb, cp, 2 * wj - 2, 2 * wi - 2, sl[1], rk[1]);
+      ptx::tma_load_5d(dst + R4 * ROWB, &tmL4, fb, cp, 3 * wj - 1, 3 * wi - 1, sl[2], rk[2]);
     };
     auto dump_tile = [&](const uint8_t* tile, int item, int which) {           // test hook: an assembled tile, de-swizzled
       __half* d = p.dump + ((static_cast<int64_t>(hp) * n_items + item) * 2 + which) * NPAD * CPAIR;
@@ -570,15 +577,29 @@ int launch_cfm(const CUtensorMap* tm, const CfmParams& p, cudaStream_t st) {
   return launch_status("cfm_attention_tc_kernel");
 }
 
-int cfm_run(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void* out, void* dump, int B, int H, int W, int C,
+// Where the pooled K/V of a launch live.  kv_tgt: pooled target level, [B, nW, 512] with clip stride tgt_stride (elements).
+// kv_ref[k]: base of the level maps of reference role k: the map of slot s of rank r starts s * slot_stride[k] +
+// r * rank_stride elements further.  ref_slot: device table [B, 3, 2] naming (slot, rank) of every clip's reference frame k,
+// or null ((clip index, 0)).
+struct CfmKv {
+  const void* kv_tgt; int64_t tgt_stride;
+  const void* kv_ref[3]; int64_t slot_stride[3]; int64_t rank_stride;
+  const int32_t* ref_slot; int n_slots[3]; int n_ranks;
+};
+
+int cfm_run(const void* qkv_a, const CfmKv& kv, const void* bias_tab, void* out, void* dump, int B, int H, int W, int C,
             int heads, float scale, void* stream, long long* prof = nullptr) {
-  CFFM_REQUIRE(qkv_a && kv_pooled && bias_tab && out, CFFM_E_BADARG, "cfm_attention: null pointer");
-  CFFM_REQUIRE(B > 0 && H > 0 && W > 0 && scale > 0.f, CFFM_E_BADARG, "cfm_attention: non-positive size or scale");
+  CFFM_REQUIRE(qkv_a && kv.kv_tgt && kv.kv_ref[0] && kv.kv_ref[1] && kv.kv_ref[2] && bias_tab && out, CFFM_E_BADARG,
+               "cfm_attention: null pointer");
+  CFFM_REQUIRE(B > 0 && H > 0 && W > 0 && scale > 0.f && kv.n_ranks > 0 && kv.n_slots[0] > 0 && kv.n_slots[1] > 0 && kv.n_slots[2] > 0,
+               CFFM_E_BADARG, "cfm_attention: non-positive size or scale");
   CFFM_REQUIRE(C == 256 && heads == 8, CFFM_E_UNSUPPORTED,
                "cfm_attention: built for C=256, heads=8 (cffm_head.py:74-95), got C=%d heads=%d", C, heads);
-  CFFM_REQUIRE(aligned16(qkv_a) && aligned16(kv_pooled) && aligned16(bias_tab) && aligned16(out), CFFM_E_BADARG,
-               "cfm_attention: pointers must be 16-byte aligned");
-  const int nWh = (H + WS - 1) / WS, nWw = (W + WS - 1) / WS, nW = nWh * nWw;
+  CFFM_REQUIRE(aligned16(qkv_a) && aligned16(kv.kv_tgt) && aligned16(kv.kv_ref[0]) && aligned16(kv.kv_ref[1]) && aligned16(kv.kv_ref[2]) &&
+                   aligned16(bias_tab) && aligned16(out) && kv.tgt_stride % 8 == 0 && kv.rank_stride % 8 == 0 &&
+                   kv.slot_stride[0] % 8 == 0 && kv.slot_stride[1] % 8 == 0 && kv.slot_stride[2] % 8 == 0,
+               CFFM_E_BADARG, "cfm_attention: pointers and strides must be 16-byte aligned");
+  const int nWh = (H + WS - 1) / WS, nWw = (W + WS - 1) / WS;
   const int64_t Ha = nWh * WS + 2 * RING, Wa = nWw * WS + 2 * RING;
   CUtensorMap tm[5];
   {
@@ -587,13 +608,21 @@ int cfm_run(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void
     int rc = make_tmap_4d(&tm[0], qkv_a, dims, strides, box);
     if (rc) return rc;
   }
-  const int lev_f[4] = {1, 1, 2, 3}, lev_k[4] = {5, 7, 5, 3}, lev_base[4] = {0, 1, 2, 6};
+  const int lev_f[4] = {1, 1, 2, 3}, lev_k[4] = {5, 7, 5, 3};
   for (int l = 0; l < 4; ++l) {
     const int64_t gw = static_cast<int64_t>(lev_f[l]) * nWw, gh = static_cast<int64_t>(lev_f[l]) * nWh;
-    const int64_t dims[4] = {CKV, gw, gh, B}, strides[3] = {CKV, gw * CKV, static_cast<int64_t>(15) * nW * CKV};
-    const int box[4] = {CPAIR, lev_k[l], lev_k[l], 1};
-    int rc = make_tmap_4d(&tm[1 + l], static_cast<const __half*>(kv_pooled) + static_cast<int64_t>(lev_base[l]) * nW * CKV, dims,
-                          strides, box);
+    int rc;
+    if (l == 0) {
+      const int64_t dims[4] = {CKV, gw, gh, B}, strides[3] = {CKV, gw * CKV, kv.tgt_stride};
+      const int box[4] = {CPAIR, lev_k[l], lev_k[l], 1};
+      rc = make_tmap_nd(&tm[1], kv.kv_tgt, 4, dims, strides, box);
+    } else {
+      // a stride of a dimension of extent 1 is never used, but the encoder still wants a 16-byte multiple > 0
+      const int64_t rs = kv.rank_stride > 0 ? kv.rank_stride : kv.slot_stride[l - 1];
+      const int64_t dims[5] = {CKV, gw, gh, kv.n_slots[l - 1], kv.n_ranks}, strides[4] = {CKV, gw * CKV, kv.slot_stride[l - 1], rs};
+      const int box[5] = {CPAIR, lev_k[l], lev_k[l], 1, 1};
+      rc = make_tmap_nd(&tm[1 + l], kv.kv_ref[l - 1], 5, dims, strides, box);
+    }
     if (rc) return rc;
   }
   CfmParams p;
@@ -602,10 +631,25 @@ int cfm_run(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void
   p.out = static_cast<__half*>(out);
   p.dump = static_cast<__half*>(dump);
   p.prof = prof;
+  p.ref_slot = kv.ref_slot;
   p.B = B; p.H = H; p.W = W; p.nWh = nWh; p.nWw = nWw;
   p.scale_log2e = scale * LOG2E;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return launch_cfm(tm, p, st);
+}
+
+// kv_pooled fp16 [B, 15 nW, 512]: the four level maps of a clip back to back (target | ref 0 | ref 1 | ref 2)
+CfmKv packed_kv(const void* kv_pooled, int B, int H, int W) {
+  const int64_t nW = static_cast<int64_t>((H + WS - 1) / WS) * ((W + WS - 1) / WS);
+  const __half* base = static_cast<const __half*>(kv_pooled);
+  CfmKv kv;
+  kv.kv_tgt = base; kv.tgt_stride = 15 * nW * CKV;
+  kv.kv_ref[0] = base ? base + nW * CKV : nullptr; kv.kv_ref[1] = base ? base + 2 * nW * CKV : nullptr;
+  kv.kv_ref[2] = base ? base + 6 * nW * CKV : nullptr;
+  for (int k = 0; k < 3; ++k) { kv.slot_stride[k] = 15 * nW * CKV; kv.n_slots[k] = B; }
+  kv.rank_stride = 0; kv.n_ranks = 1;
+  kv.ref_slot = nullptr;
+  return kv;
 }
 
 }  // namespace
@@ -613,13 +657,28 @@ int cfm_run(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void
 
 extern "C" int cffm_cfm_attention(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void* out, int B, int H,
                                   int W, int C, int heads, float scale, void* stream) {
-  return cffm::cfm_run(qkv_a, kv_pooled, bias_tab, out, nullptr, B, H, W, C, heads, scale, stream);
+  return cffm::cfm_run(qkv_a, cffm::packed_kv(kv_pooled, B, H, W), bias_tab, out, nullptr, B, H, W, C, heads, scale, stream);
+}
+
+extern "C" int cffm_cfm_attention_slots(const void* qkv_a, const void* kv_tgt, int64_t tgt_stride, const void* kv_ref0,
+                                        const void* kv_ref1, const void* kv_ref2, int64_t slot_stride0, int64_t slot_stride1,
+                                        int64_t slot_stride2, int n_slots0, int n_slots1, int n_slots2, int64_t rank_stride,
+                                        int n_ranks, const int32_t* ref_slot, const void* bias_tab, void* out, int B, int H,
+                                        int W, int C, int heads, float scale, void* stream) {
+  cffm::CfmKv kv;
+  kv.kv_tgt = kv_tgt; kv.tgt_stride = tgt_stride;
+  kv.kv_ref[0] = kv_ref0; kv.kv_ref[1] = kv_ref1; kv.kv_ref[2] = kv_ref2;
+  kv.slot_stride[0] = slot_stride0; kv.slot_stride[1] = slot_stride1; kv.slot_stride[2] = slot_stride2;
+  kv.n_slots[0] = n_slots0; kv.n_slots[1] = n_slots1; kv.n_slots[2] = n_slots2;
+  kv.rank_stride = rank_stride; kv.n_ranks = n_ranks;
+  kv.ref_slot = ref_slot;
+  return cffm::cfm_run(qkv_a, kv, bias_tab, out, nullptr, B, H, W, C, heads, scale, stream);
 }
 
 extern "C" int cffm_cfm_attention_dump(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void* out, void* dump,
                                        int B, int H, int W, int C, int heads, float scale, void* stream) {
   CFFM_REQUIRE(dump != nullptr, CFFM_E_BADARG, "cfm_attention_dump: null dump buffer");
-  return cffm::cfm_run(qkv_a, kv_pooled, bias_tab, out, dump, B, H, W, C, heads, scale, stream);
+  return cffm::cfm_run(qkv_a, cffm::packed_kv(kv_pooled, B, H, W), bias_tab, out, dump, B, H, W, C, heads, scale, stream);
 }
 
 extern "C" int cffm_cfm_layout(int32_t* out8) {
@@ -633,5 +692,6 @@ extern "C" int cffm_cfm_layout(int32_t* out8) {
 /* Bring-up hook (not in the header): SM-clock stamps of the pipeline events of the first 8 items of every CTA. */
 extern "C" int cffm_cfm_attention_prof(const void* qkv_a, const void* kv_pooled, const void* bias_tab, void* out, void* prof,
                                        int B, int H, int W, int C, int heads, float scale, void* stream) {
-  return cffm::cfm_run(qkv_a, kv_pooled, bias_tab, out, nullptr, B, H, W, C, heads, scale, stream, static_cast<long long*>(prof));
+  return cffm::cfm_run(qkv_a, cffm::packed_kv(kv_pooled, B, H, W), bias_tab, out, nullptr, B, H, W, C, heads, scale, stream,
+                       static_cast<long long*>(prof));
 }

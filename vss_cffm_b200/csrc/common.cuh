@@ -60,6 +60,7 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 // 2-D fp16 row-major [rows, K] tensor map, row stride ld (elements); box = [box_rows][64], 128-byte swizzle.
 // `tm` is a CUtensorMap* (kept as void* here so that this header does not pull in <cuda.h>).
 int make_tmap(struct CUtensorMap_st* tm, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows);
+int make_tmap_nd(struct CUtensorMap_st* tm, const void* base, int rank, const int64_t* dims, const int64_t* strides, const int* box);
 int make_tmap_4d(struct CUtensorMap_st* tm, const void* base, const int64_t dims[4], const int64_t strides[3], const int box[4]);
 int num_sms();
 

@@ -498,23 +498,25 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t K, int64_
   return CFFM_OK;
 }
 
-// 4-D fp16 tensor map, 128-byte swizzle: dims / box innermost first, strides (elements) of dims 1..3.  The innermost box
-// extent must be 64 elements (one 128-byte swizzled row per box position).  Shared: common.cuh.
-int make_tmap_4d(CUtensorMap* tm, const void* base, const int64_t dims[4], const int64_t strides[3], const int box[4]) {
+// rank-D (3..5) fp16 tensor map, 128-byte swizzle: dims / box innermost first, strides (elements) of dims 1..rank-1.  The
+// innermost box extent must be 64 elements (one 128-byte swizzled row per box position).  Shared: common.cuh.
+int make_tmap_nd(CUtensorMap* tm, const void* base, int rank, const int64_t* dims, const int64_t* strides, const int* box) {
   EncodeTiledFn fn = get_encode_fn();
   CFFM_REQUIRE(fn != nullptr, CFFM_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t gdim[4], gstride[3];
-  cuuint32_t bx[4], estr[4] = {1, 1, 1, 1};
-  for (int i = 0; i < 4; ++i) { gdim[i] = static_cast<cuuint64_t>(dims[i]); bx[i] = static_cast<cuuint32_t>(box[i]); }
-  for (int i = 0; i < 3; ++i) gstride[i] = static_cast<cuuint64_t>(strides[i]) * 2;
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstride, bx, estr,
+  CFFM_REQUIRE(rank >= 3 && rank <= 5, CFFM_E_BADARG, "make_tmap_nd: rank %d", rank);
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t bx[5], estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gdim[i] = static_cast<cuuint64_t>(dims[i]); bx[i] = static_cast<cuuint32_t>(box[i]); }
+  for (int i = 0; i + 1 < rank; ++i) gstride[i] = static_cast<cuuint64_t>(strides[i]) * 2;
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstride, bx, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  CFFM_REQUIRE(r == CUDA_SUCCESS, CFFM_E_DRIVER,
-               "cuTensorMapEncodeTiled (4-D) failed with CUresult %d (dims %lld %lld %lld %lld, box %d %d %d %d)",
-               static_cast<int>(r), (long long)dims[0], (long long)dims[1], (long long)dims[2], (long long)dims[3], box[0],
-               box[1], box[2], box[3]);
+  CFFM_REQUIRE(r == CUDA_SUCCESS, CFFM_E_DRIVER, "cuTensorMapEncodeTiled (%d-D) failed with CUresult %d (dims %lld %lld %lld ..., box %d %d %d ...)",
+               rank, static_cast<int>(r), (long long)dims[0], (long long)dims[1], (long long)dims[2], box[0], box[1], box[2]);
   return CFFM_OK;
+}
+int make_tmap_4d(CUtensorMap* tm, const void* base, const int64_t dims[4], const int64_t strides[3], const int box[4]) {
+  return make_tmap_nd(tm, base, 4, dims, strides, box);
 }
 
 // fp16 [rows, cols] output (row stride ld elements) as the target of per-warp 32 x 32 bulk stores (64-byte swizzle).

@@ -260,6 +260,28 @@ def cfm_attention(qkv_a, kv_pooled, bias_tab, out, B, H, W, C, heads, scale, dum
                   heads, float(scale), _stream())
 
 
+def cfm_attention_slots(qkv_a, kv_tgt, gathered, role_off, role_slots, ref_slot, bias_tab, out, B, H, W, C, heads, scale):
+    """CFM attention reading the reference-frame K/V in place from the all-gathered buffer (frame-sharded path).
+    kv_tgt fp16 [B, nW, 2C] contiguous; gathered fp16 [n_ranks, flat_tokens, 2C] (a view: dim-0 stride = rank stride) in
+    which the maps of reference role k start at token role_off[k], role_slots[k] of them per rank, {1,4,9}[k] nW tokens each;
+    ref_slot int32 [B, 3, 2] = (slot, rank) on the device."""
+    _chk(qkv_a, _H, "cfm.qkv_a"); _chk(kv_tgt, _H, "cfm.kv_tgt"); _chk(gathered, _H, "cfm.gathered"); _chk(bias_tab, _H, "cfm.bias_tab")
+    _chk(out, _H, "cfm.out")
+    nW = ((H + 6) // 7) * ((W + 6) // 7)
+    assert kv_tgt.is_contiguous() and kv_tgt.numel() == B * nW * 2 * C
+    assert gathered.dim() == 3 and gathered.shape[2] == 2 * C and gathered.stride(1) == 2 * C
+    per = (1, 4, 9)
+    assert all(role_off[k] + role_slots[k] * per[k] * nW <= gathered.shape[1] for k in range(3))
+    assert ref_slot.dtype == torch.int32 and ref_slot.is_cuda and ref_slot.is_contiguous() and tuple(ref_slot.shape) == (B, 3, 2)
+    assert qkv_a.numel() == apron_rows(B, H, W) * 3 * C and out.numel() == B * H * W * C
+    base, es = gathered.data_ptr(), gathered.element_size()
+    _abi.call("cffm_cfm_attention_slots", _ptr(qkv_a), _ptr(kv_tgt), nW * 2 * C,
+              base + role_off[0] * 2 * C * es, base + role_off[1] * 2 * C * es, base + role_off[2] * 2 * C * es,
+              per[0] * nW * 2 * C, per[1] * nW * 2 * C, per[2] * nW * 2 * C, max(role_slots[0], 1), max(role_slots[1], 1),
+              max(role_slots[2], 1), gathered.stride(0), gathered.shape[0], _ptr(ref_slot), _ptr(bias_tab), _ptr(out), B, H, W, C,
+              heads, float(scale), _stream())
+
+
 def resize_nhwc_to_nchw(x, ncls, out, B, h, w, Ho, Wo):
     assert x.dtype in (_H, _F)
     _chk(x, x.dtype, "resize.x"); _chk(out, _F, "resize.out")

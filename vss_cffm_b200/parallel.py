@@ -10,10 +10,11 @@ Two ways the path shards:
    reading, for every block, the pooled K/V of the three reference frames (cffm_transformer.py:780-805, :470-518).
    Reference frames are never modified by a block (:826), so the owner of reference frame (b, t) can compute
    LN -> role-t pooling -> K/V projection for ALL blocks up front.  ``FrameShardedRunner`` does exactly that, then
-   issues ONE all-gather of the packed per-frame K/V ([depth, 729, 512] fp16 per reference frame, 81/324/729 tokens
-   used for role 0/1/2) and the owners of the target frames run the CFM attention + FFN locally.
-   The payload is ~1.5 MB per reference frame: latency-bound on NVLink, so it is a single NCCL call, not a fused
-   kernel (there is no compute to overlap it with on the target-owner's critical path except its own QKV GEMM).
+   issues ONE all-gather of the packed K/V (per rank and block: its role-0 / 1 / 2 maps of 81 / 324 / 729 tokens x 512 fp16
+   back to back, nothing padded) on a side stream, and the owners of the target frames run the CFM attention + FFN
+   locally; the CFM kernel reads the gathered buffer in place through a per-clip (slot, rank) table.
+   The payload is ~1.2 MB per clip and block: latency-bound on NVLink, so it is a single NCCL call hidden behind the
+   target frames' norm1 / pooling / QKV GEMM, not a fused kernel.
 
 Ownership: frame (b, t) of a global batch of Bg clips lives on rank (b + t) mod G when Bg >= G (every rank then owns
 Bg/G frames of each temporal role, i.e. Bg/G targets: balanced) and on rank (b*T + t) mod G otherwise.
@@ -50,6 +51,17 @@ class FrameShardPlan:
         self.targets = [[b for b, t in fr if t == n_frames - 1] for fr in self.frames]
         self.max_slots = max(1, max(len(r) for r in self.refs))
         self._slot = {f: (rank, i) for rank, r in enumerate(self.refs) for i, f in enumerate(r)}
+        # per temporal role k: how many reference frames a rank owns at most, and where frame (b, k) sits among its owner's
+        # role-k frames.  Every rank packs its role-k K/V maps back to back (role_slots[k] maps of {1,4,9}[k] nW tokens), so the
+        # all-gather moves exactly the tokens the CFM kernel reads (no padding of role 0 / 1 frames to the role-2 size).
+        self.role_count = [[sum(1 for f in r if f[1] == k) for k in range(n_frames - 1)] for r in self.refs]
+        self.role_slots = [max(1, max(c[k] for c in self.role_count)) for k in range(n_frames - 1)]
+        self._role_index = {}
+        for rank, r in enumerate(self.refs):
+            seen = [0] * (n_frames - 1)
+            for (b, t) in r:
+                self._role_index[(b, t)] = (seen[t], rank)
+                seen[t] += 1
 
     def owner(self, b, t):
         return (b + t) % self.G if self.Bg >= self.G else (b * self.T + t) % self.G
@@ -57,6 +69,18 @@ class FrameShardPlan:
     def slot_of(self, b, t):
         """(owner rank, slot index in that rank's send buffer) of reference frame (b, t)."""
         return self._slot[(b, t)]
+
+    def role_index(self, b, t):
+        """(index among the owner's role-t frames, owner rank) of reference frame (b, t)."""
+        return self._role_index[(b, t)]
+
+    def role_offsets(self, nW):
+        """Token offset of every role's block in a rank's packed buffer, and the buffer's token count."""
+        off, o = [], 0
+        for k, per in enumerate(ROLE_TOKENS):
+            off.append(o)
+            o += self.role_slots[k] * per * nW
+        return off, o
 
     def gathered_index(self, b, t):
         """Row of reference frame (b, t) in the all-gathered buffer [G * max_slots, ...]."""
@@ -76,7 +100,8 @@ def all_gather_slots(send, group=None):
 
 
 def assemble_kv(plan, gathered, clip, block, nW, out):
-    """Copy the K/V of clip ``clip``'s three reference frames for ``block`` from the gathered buffer
+    """Host-side reference of what the slot table means (the runner itself copies nothing: ``cffm_cfm_attention_slots`` reads
+    the gathered buffer in place).  Copy the K/V of clip ``clip``'s three reference frames for ``block`` from the gathered buffer
     [G*max_slots, depth, 9 nW, 2C] into ``out`` [15 nW, 2C] behind the nW pooled-target rows (layout of
     cffm_cfm_attention's kv_pooled: target | ref0 | ref1 | ref2)."""
     off = nW
@@ -93,6 +118,14 @@ class FrameShardedRunner:
     def __init__(self, model, plan, rank, group=None):
         self.model, self.plan, self.rank, self.group = model, plan, rank, group
         self.ws = Workspace()
+
+    def _slot_table(self, dev):
+        """int32 [n_targets, 3, 2] on the device: (index among the owner's role-t maps, owner rank) of reference frame t of each
+        target clip of this rank."""
+        if getattr(self, "_slots", None) is None or self._slots.device != dev:
+            rows = [[list(self.plan.role_index(clip, t)) for t in range(3)] for clip in self.plan.targets[self.rank]]
+            self._slots = torch.tensor(rows, dtype=torch.int32).reshape(-1, 3, 2).to(dev)
+        return self._slots
 
     def local_frames(self):
         """[(clip, t)] this rank must be fed, in the order ``run`` expects them."""
@@ -116,11 +149,12 @@ class FrameShardedRunner:
             feats = [head._as_nhwc16(t) for t in model.backbone(frames)]   # no stage hook: projections are issued below
             sizes = [(t.shape[1], t.shape[2]) for t in feats]
             h, w = sizes[0]
-            proj = []
-            for i, t in enumerate(feats):
-                p = ws.get(f"p{i}", (n_loc * sizes[i][0] * sizes[i][1], E), _H, device=dev)
-                ops.gemm(t.reshape(-1, t.shape[3]), P["pw"][i], out16=p)
-                proj.append(p)
+            proj = [ws.get(f"p{i}", (n_loc * sizes[i][0] * sizes[i][1], E), _H, device=dev) for i in range(4)]
+            with ops.fork():                                     # the three small projections beside the big one
+                for i in (1, 2, 3):
+                    ops.gemm(feats[i].reshape(-1, feats[i].shape[3]), P["pw"][i], out16=proj[i])
+            ops.gemm(feats[0].reshape(-1, feats[0].shape[3]), P["pw"][0], out16=proj[0])
+            ops.join()
         else:
             h, w = (H - 1) // 4 + 1, (W - 1) // 4 + 1              # OverlapPatchEmbed k7 s4 p3 (mix_transformer.py:173-195): same on every rank
         h2, w2 = h // 2, w // 2
@@ -131,20 +165,33 @@ class FrameShardedRunner:
         c16 = ws.get("c16", (max(n_loc, 1) * HW, E), _H, device=dev)
         if n_loc:
             ops.head_fuse(proj, sizes, n_loc, E, 0, P["shift"], half32=x32, half16=c16)
-        # ---- reference frames: K/V of every block, packed for the exchange (cffm_transformer.py:780-805, :495-518)
-        send = ws.get("send", (plan.max_slots, depth, 9 * nW, 2 * E), _H, device=dev, zero=True)
+        # ---- reference frames: K/V of every block, packed for the exchange (cffm_transformer.py:780-805, :495-518).  The local
+        # frames are frame-major, so the reference frames of one temporal role are contiguous: one pooling launch per role and
+        # ONE K/V projection per block over the rank's packed [role 0 maps | role 1 maps | role 2 maps] token buffer.
+        role_off, flat_tok = plan.role_offsets(nW)
+        send = ws.get("send", (depth, flat_tok, 2 * E), _H, device=dev, zero=True)
         if n_ref:
             xn = ws.get("xn_ref", (n_ref * HW, E), _H, device=dev)
+            pooled = ws.get("pooled_refs", (flat_tok, E), _H, device=dev, zero=True)     # rows of unused slots stay zero
             for i, b in enumerate(P["blocks"]):
                 ops.cffa_norm_frames(x32[:n_ref * HW], b["n1g"], b["n1b"], b["n1eps"], xn, None, n_ref, n_ref, h2, w2, Hp, Wp, E)
-                for slot, (_, t) in enumerate(plan.refs[self.rank]):
-                    n = ROLE_TOKENS[t] * nW
-                    pooled = ws.get(f"pooled_r{t}", (n, E), _H, device=dev)
-                    ops.cffa_pool_level(xn[slot * HW:(slot + 1) * HW], 1, t + 1, h2, w2, E, b["pool_w"], b["pool_b"], pooled)
-                    ops.gemm(pooled, b["qkv_w"][E:], bias=b["qkv_b"][E:], out16=send[slot, i, :n])
-        # ---- the one collective of the path
-        gathered = all_gather_slots(send, self.group) if plan.G > 1 else send
+                first = 0
+                for k, per in enumerate(ROLE_TOKENS):
+                    n_k = plan.role_count[self.rank][k]
+                    if n_k:
+                        ops.cffa_pool_level(xn[first * HW:(first + n_k) * HW], n_k, k + 1, h2, w2, E, b["pool_w"], b["pool_b"],
+                                            pooled[role_off[k]:role_off[k] + n_k * per * nW])
+                    first += n_k
+                ops.gemm(pooled, b["qkv_w"][E:], bias=b["qkv_b"][E:], out16=send[i])
+        # ---- the one collective of the path, on a side stream: it overlaps norm1 / pooling / the QKV GEMM of the first block
+        # (SURVEY.md 8e); the CFM kernel then reads the gathered buffer IN PLACE through a per-clip slot table
+        if plan.G > 1:
+            with ops.fork("gather"):
+                gathered = all_gather_slots(send, self.group).view(plan.G, depth, flat_tok, 2 * E)
+        else:
+            gathered = send.view(1, depth, flat_tok, 2 * E)
         if not n_t:
+            ops.join("gather")
             return torch.empty(0, H, W, dtype=torch.int64, device=dev)
         # ---- target frames: CFFM blocks (cffm_transformer.py:709-832) with the gathered reference K/V
         xt = x32[n_ref * HW:(n_ref + n_t) * HW]
@@ -154,20 +201,20 @@ class FrameShardedRunner:
         pooled_t = ws.get("pooled_t", (n_t * nW, E), _H, device=dev)
         kv_t = ws.get("kv_t", (n_t * nW, 2 * E), _H, device=dev)
         qkv_t = ws.get("qkv_t", (ops.apron_rows(n_t, h2, w2), 3 * E), _H, device=dev)
-        kvp = ws.get("kvp", (n_t, 15 * nW, 2 * E), _H, device=dev)
         ao = ws.get("ao", (n_t * HW, E), _H, device=dev)
         xn2 = ws.get("xn2", (n_t * HW, E), _H, device=dev)
         hid = ws.get("hid", (n_t * HW, 4 * E), _H, device=dev)
         xt16 = ws.get("xt16", (n_t * HW, E), _H, device=dev)
+        slots = self._slot_table(dev)
         for i, b in enumerate(P["blocks"]):
             ops.cffa_norm_frames(xt, b["n1g"], b["n1b"], b["n1eps"], xn_t, xt_pad, n_t, 0, h2, w2, Hp, Wp, E)
             ops.cffa_pool_level(xn_t, n_t, 0, h2, w2, E, b["pool_w"], b["pool_b"], pooled_t)
             ops.gemm(xt_pad, b["qkv_w"], bias=b["qkv_b"], out16=qkv_t)
             ops.gemm(pooled_t, b["qkv_w"][E:], bias=b["qkv_b"][E:], out16=kv_t)
-            kvp[:, :nW].copy_(kv_t.view(n_t, nW, 2 * E))
-            for j, clip in enumerate(plan.targets[self.rank]):
-                assemble_kv(plan, gathered, clip, i, nW, kvp[j])
-            ops.cfm_attention(qkv_t, kvp.view(n_t * 15 * nW, 2 * E), b["bias"], ao, n_t, h2, w2, E, HEADS, (E // HEADS) ** -0.5)
+            if i == 0:
+                ops.join("gather")
+            ops.cfm_attention_slots(qkv_t, kv_t, gathered[:, i], role_off, plan.role_slots, slots, b["bias"], ao, n_t, h2, w2, E, HEADS,
+                                    (E // HEADS) ** -0.5)
             ops.gemm(ao, b["proj_w"], bias=b["proj_b"], residual=xt, out32=xt)
             ops.layernorm(xt, b["n2g"], b["n2b"], b["n2eps"], out16=xn2)
             ops.gemm(xn2, b["f1w"], bias=b["f1b"], out16=hid, act=ops.ACT_GELU)
@@ -209,6 +256,14 @@ class GraphedFrameShard:
         self.kernels_per_replay = _abi.n_launches - n0
         for ws in [runner.ws] + runner.model.workspaces():       # the graph replays on these addresses: never free them
             ws.pin()
+
+    def close(self):
+        """Release the captured graph (it holds the communicator's resources: destroy_process_group() hangs while a graph
+        with a captured collective is alive)."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
 
     def replay(self):
         self.graph.replay()
