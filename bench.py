@@ -9,8 +9,9 @@ synthetic N(0,1) frames, synthetic weights (vss_cffm_b200.synth), 124 classes.  
 EncoderDecoder_clips inference pass over one batch: frames -> int64 label maps.
 
   value : clip-frames/s (B*T*N / max-over-ranks device time), inputs resident in HBM, labels left in HBM
-  e2e   : same metric through the public API with HOST (pinned) frames: H2D copy, forward, D2H of labels
-          inside the timed region
+  e2e   : same metric through the public API with HOST (pinned) DECODED frames (uint8): H2D copy, preprocessing,
+          forward, D2H of the labels inside the timed region (e2e_from_fp32_tensors: fed normalised fp32 tensors;
+          e2e_mmseg_call: the reference-facing model(img=..., return_loss=False) call itself)
   roofline     : the dominant kernel family (tcgen05 GEMM) and, separately, the CFM attention kernel the metric
                  names, both timed live with CUDA events around each launch
   cpu_baseline : the CPU oracle (a port of the reference's PyTorch path) on this box's host cores, bounded sample
@@ -36,7 +37,9 @@ H = W = 480
 T = 4
 CLIPS_PER_GPU = 2
 VARIANT = "b1"
-HEAD_DEPTH = {"b0": 1, "b1": 2, "b2": 2}                            # local_configs/cffm/B*/: decoder_params.depths
+HEAD_DEPTH = {"b0": 1, "b1": 2, "b2": 2, "b5": 4}                   # local_configs/cffm/B*/: decoder_params.depths
+KIND = "cffm"
+PROTOS = 0
 CFM_FLOPS_PER_CLIP_BLOCK = 2 * 2 * 81 * 8 * 49 * 289 * 32            # QK^T + PV, SURVEY.md 8(d): 1.1746 GFLOP
 # fp16 operands each once, per clip per block: Q + target K,V + pooled K,V + O + bias tables
 CFM_BYTES_PER_CLIP_BLOCK = (3969 * 256 * 2) + (3969 * 512 * 2) + (1215 * 512 * 2) + (3600 * 256 * 2) + (8 * 49 * 289 * 4)
@@ -49,8 +52,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shard", default="clips", choices=["clips", "frames"])
-    ap.add_argument("--variant", default="b1", choices=["b0", "b1", "b2"],
-                    help="MiT backbone; b1 is the headline workload (BASELINE configs[1]), b2 = configs[3]")
+    ap.add_argument("--variant", default="b1", choices=["b0", "b1", "b2", "b5"],
+                    help="MiT backbone; b1 is the headline workload (BASELINE configs[1]), b2 = configs[3], b0 with --clips 1 --T 2 = configs[0]")
+    ap.add_argument("--clips", type=int, default=2, help="clips per GPU and step (headline: 2)")
+    ap.add_argument("--T", type=int, default=4, help="frames per clip; T != 4 takes the head's early-return path (configs[0]: T = 2)")
+    ap.add_argument("--kind", default="cffm", choices=["cffm", "cffmpp"], help="cffmpp = CFFM++ head with k-means prototypes (configs[4])")
+    ap.add_argument("--protos", type=int, default=64, help="prototypes per clip for --kind cffmpp (configs[4]: 64; README: 100)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -114,7 +121,7 @@ def oracle_state(seed=21):
     """Weights for the CPU oracle: the same synthetic state dict the GPU model is filled with."""
     import vss_cffm_b200 as V
     from vss_cffm_b200 import synth
-    m = V.build_segmentor(V.model_cfg(VARIANT))
+    m = V.build_segmentor(V.model_cfg(VARIANT, KIND))
     synth.fill_module(m, seed)
     return m, {k: v.clone() for k, v in m.state_dict().items()}
 
@@ -129,12 +136,13 @@ def cpu_reference_time(sd, steps, warmup, clips=1):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     imgs = synth.synth_clip(clips, T, H, W, seed=3)
+    centers = synth.synth_array((clips, PROTOS, 256), 77) if KIND == "cffmpp" else None
     for _ in range(warmup):
-        O.segmentor_simple_test(sd, imgs, "mit_" + VARIANT, HEAD_DEPTH[VARIANT])
+        O.segmentor_simple_test(sd, imgs, "mit_" + VARIANT, HEAD_DEPTH[VARIANT], centers=centers)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        O.segmentor_simple_test(sd, imgs, "mit_" + VARIANT, HEAD_DEPTH[VARIANT]).numpy()
+        O.segmentor_simple_test(sd, imgs, "mit_" + VARIANT, HEAD_DEPTH[VARIANT], centers=centers).numpy()
         ts.append(time.perf_counter() - t0)
     mean = sum(ts) / len(ts)
     return clips * T / mean, mean * 1e3, torch.get_num_threads()
@@ -151,7 +159,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": 1, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"MiT-{VARIANT.upper()} + CFFM (depth {HEAD_DEPTH[VARIANT]}), {H}x{W}, T={T}, reference's PyTorch path on host CPU cores",
+        "config": {"workload": f"MiT-{VARIANT.upper()} + CFFM{'++ (K=%d)' % PROTOS if KIND == 'cffmpp' else ''} (depth {HEAD_DEPTH[VARIANT]}), {H}x{W}, T={T}, reference's PyTorch path on host CPU cores",
                    "note": "the reference is pure Python/PyTorch+mmcv (mmcv absent offline); this is oracle/cffm_oracle.py, the "
                            "CPU port pinned to goldens generated from the unmodified reference"},
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -234,9 +242,10 @@ def measure_frame_shard(args, model, rank, world, B, flush, clip_ms):
 
 def main():
     args = parse()
-    global VARIANT, METRIC
-    VARIANT = args.variant
-    METRIC = f"clip-frames/sec (480x480, T=4, MiT-{VARIANT.upper()}+CFFM)"
+    global VARIANT, METRIC, T, CLIPS_PER_GPU, KIND, PROTOS
+    VARIANT, T, CLIPS_PER_GPU, KIND = args.variant, args.T, args.clips, args.kind
+    PROTOS = args.protos if KIND == "cffmpp" else 0
+    METRIC = f"clip-frames/sec (480x480, T={T}, MiT-{VARIANT.upper()}+CFFM{'++' if KIND == 'cffmpp' else ''})"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -268,10 +277,13 @@ def main():
     labels_host = torch.empty(B, H, W, dtype=torch.int64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
+    # CFFM++ (configs[4]): the prototypes of each clip's video are an INPUT of the head (k-means centres loaded from
+    # <save_path>/<video>/centers.pt in the reference, cffm_head.py:429-455); the bench feeds synthetic ones
+    head_kw = dict(centers=synth.synth_array((B, PROTOS, 256), 77).cuda()) if KIND == "cffmpp" else {}
     graphed = None
     gfs = None
     frames_graph_nodes = None
-    frames_mode = args.shard == "frames" and world > 1
+    frames_mode = args.shard == "frames" and world > 1 and T == 4 and KIND == "cffm"
     if frames_mode:
         # the global batch (B clips per GPU x world) with its FRAMES spread over the ranks; one NCCL all-gather of the
         # reference-frame K/V per step (vss_cffm_b200/parallel.py).  Launched eagerly (the collective is not captured).
@@ -292,11 +304,11 @@ def main():
             except Exception as e:                               # capture of the collective refused: stay eager, say so
                 print(f"rank {rank}: frame-sharded pass not captured ({type(e).__name__}: {e}); launching eagerly", file=sys.stderr)
     else:
-        step_eager = lambda: model.predict_labels(imgs_dev, metas)
+        step_eager = lambda: model.predict_labels(imgs_dev, metas, **head_kw)
         if args.no_graph:
             step_dev = step_eager
         else:
-            graphed = model.make_graphed(B, T, H, W, metas)      # one cudaGraphLaunch per step
+            graphed = model.make_graphed(B, T, H, W, metas, **head_kw)      # one cudaGraphLaunch per step
             graphed.load(imgs_dev)
             step_dev = graphed.replay
 
@@ -309,7 +321,7 @@ def main():
         if graphed is not None:
             lab = graphed(imgs_host)                              # H2D of the pinned frames + graph replay
         else:
-            lab = model.predict_labels(imgs_host, metas)
+            lab = model.predict_labels(imgs_host, metas, **head_kw)
         labels_host.copy_(lab, non_blocking=True)
         return lab
 
@@ -351,7 +363,7 @@ def main():
         # copies its own frames from pinned host memory and reads its own labels back; the L2 flush runs INSIDE the
         # timed region (on the compute stream), so the number is a lower bound of the throughput.
         from vss_cffm_b200.graph import ClipPipeline
-        pipe = ClipPipeline(model, B, T, H, W, metas)
+        pipe = ClipPipeline(model, B, T, H, W, metas, head_kw=head_kw)
         hosts = [imgs_host] + [[t.pin_memory() for t in synth.synth_clip(B, T, H, W, seed=200 + 7 * i + rank)] for i in (1, 2)]
         labs = [torch.empty(B, H, W, dtype=torch.int64).pin_memory() for _ in range(3)]
 
@@ -370,7 +382,7 @@ def main():
 
         pipelined(3)
         # the pipelined labels must be the labels of the plain call on the same frames
-        chk = model.predict_labels(hosts[2], metas)
+        chk = model.predict_labels(hosts[2], metas, **head_kw)
         torch.cuda.synchronize()
         assert torch.equal(chk.cpu(), labs[2]), "pipelined labels differ from the direct call"
         barrier()
@@ -383,7 +395,7 @@ def main():
         # the headline e2e (whose input is the fp32 tensor the reference model itself receives).
         from vss_cffm_b200.preprocess import ClipPreprocessor
         pre = ClipPreprocessor()
-        pipe = ClipPipeline(model, B, T, H, W, metas, preprocessor=pre, src_hw=(H, W))
+        pipe = ClipPipeline(model, B, T, H, W, metas, head_kw=head_kw, preprocessor=pre, src_hw=(H, W))
         g8 = torch.Generator().manual_seed(300 + rank)
         hosts = [torch.randint(0, 256, (T, B, H, W, 3), dtype=torch.uint8, generator=g8).pin_memory() for _ in range(3)]
         pipelined(3)
@@ -396,8 +408,25 @@ def main():
 
     # ---- streaming with temporal re-use (vss_cffm_b200/streaming.py; not the headline: the clips of the headline metric
     # are independent).  One step = the next frame of each of B videos; labels are bit-identical to the stateless path.
+    # ---- the reference-facing call itself: model(img=[[T x (B,3,H,W)]], img_metas=[[...]], return_loss=False) -> list of numpy
+    # label maps.  From the second call on it replays a cached CUDA graph (segmentor._cached_graph); every call still copies
+    # its frames from host memory and returns host arrays, one call at a time (no overlap between calls).
+    mmseg_call = None
+    if not frames_mode and KIND == "cffm":
+        for _ in range(3):
+            model(img=[imgs_host], img_metas=[metas], return_loss=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            model(img=[imgs_host], img_metas=[metas], return_loss=False)
+        mm_ms = (time.perf_counter() - t0) * 1e3
+        mmseg_call = {"value": round(B * T * args.steps / (mm_ms * 1e-3), 2), "unit": UNIT, "ms_per_call": round(mm_ms / args.steps, 4),
+                      "api": "EncoderDecoder_clips.forward(img, img_metas, return_loss=False) -> list[np.ndarray]; cached CUDA graph, "
+                             "host wall clock, no L2 flush, one call at a time",
+                      "cached_graphs": len(getattr(model, "_graphs", {}))}
+    barrier()
     streaming = None
-    if not frames_mode:
+    if not frames_mode and T == 4 and KIND == "cffm":
         from vss_cffm_b200.streaming import VideoStream
         vs = VideoStream(model, B, graph=True)
         vframes = [imgs_dev[t % T] for t in range(8)]
@@ -433,7 +462,7 @@ def main():
     # ---- N > 1: the frame-sharded split of BASELINE configs[2] next to the clip-sharded headline: the frames of the SAME
     # global batch spread over the ranks, one NCCL all-gather of the reference-frame K/V per step (vss_cffm_b200/parallel.py)
     frame_shard = None
-    if world > 1 and not frames_mode:
+    if world > 1 and not frames_mode and T == 4 and KIND == "cffm":
         frame_shard = measure_frame_shard(args, model, rank, world, B, flush, total_ms)
     t = torch.tensor([total_ms, e2e_ms, e2e_serial_ms, e2e_u8_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -484,13 +513,13 @@ def main():
                                     "frac": round(v[2] / (v[1] / v[0] * 1e-3) / 1e9 / pk["hbm"], 4)} for k, v in top],
                     "note": "K <= 256 for nearly every GEMM of the path (AI 30-120 FLOP/B < ridge 210): HBM is the roof. "
                             "Timed live with CUDA events around each launch of an eagerly launched step whose launches are queued behind a spin kernel (no host launch gaps inside the events)."}
-        cfm_ms = [ms for name, a, ms in krec if name == "cffm_cfm_attention"]
-        cfm_avg_ms = sum(cfm_ms) / max(len(cfm_ms), 1)
+        cfm_ms = [ms for name, a, ms in krec if name in ("cffm_cfm_attention", "cffm_cfm_attention_slots")]
+        cfm_avg_ms = sum(cfm_ms) / max(len(cfm_ms), 1) if cfm_ms else float("nan")
         alg_bytes = CFM_BYTES_PER_CLIP_BLOCK * B                              # one launch = B clips of one block
         alg_flops = CFM_FLOPS_PER_CLIP_BLOCK * B
         cgbs = alg_bytes / (cfm_avg_ms * 1e-3) / 1e9
         ctfs = alg_flops / (cfm_avg_ms * 1e-3) / 1e12
-        roofline_cfm = {"kernel": "cfm_attention_tc_kernel", "bound": "hbm", "achieved": round(cgbs, 2), "peak": pk["hbm"],
+        roofline_cfm = None if not cfm_ms else {"kernel": "cfm_attention_tc_kernel", "bound": "hbm", "achieved": round(cgbs, 2), "peak": pk["hbm"],
                         "unit": "GB/s", "frac": round(cgbs / pk["hbm"], 5), "traffic": ncu_traffic("cfm_attention_tc_kernel"),
                         "tensor_tflops": round(ctfs, 3), "tensor_frac_of_sustained": round(ctfs / pk["tf_sust"], 5),
                         "launch_ms": round(cfm_avg_ms, 5), "launches_timed": len(cfm_ms),
@@ -498,21 +527,34 @@ def main():
                         "algorithmic": {"bytes_per_launch": alg_bytes, "flops_per_launch": alg_flops,
                                         "note": "SURVEY.md 8(d): 9.6 MB and 1.1746 GFLOP per clip per block; un-fused attention "
                                                 "has AI 122 FLOP/B < ridge 210, so HBM is the binding roof"}}
+        # e2e headline: the pipeline fed DECODED frames (uint8, what the reference's loader hands to its transforms) when that
+        # path ran; the same pipeline fed the normalised fp32 tensors the reference MODEL receives is reported beside it
+        e2e_fp32 = {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms / args.steps, 4),
+                    "h2d_bytes_per_step": B * T * 3 * H * W * 4, "d2h_bytes_per_step": B * H * W * 8, "api": e2e_api,
+                    "input": "normalised fp32 frames (T x (B,3,H,W)), pinned host memory",
+                    "serial_value": round(frames / (e2e_serial_ms * 1e-3), 2),
+                    "serial_api": "graph.load(pinned host frames) -> replay -> D2H labels, one step at a time (no overlap)"}
+        e2e_main = e2e_fp32
+        if e2e_u8:
+            e2e_main = dict(e2e_u8, value=round(frames / (e2e_u8_ms * 1e-3), 2), ms_per_step=round(e2e_u8_ms / args.steps, 4),
+                            input="decoded uint8 BGR HWC frames (T,B,H,W,3), pinned host memory; AlignedResize_clips / Normalize_clips / "
+                                  "ImageToTensor_clips run on the GPU inside the captured pass (bit-exact with cv2 / mmcv)",
+                            serial_value=e2e_fp32["serial_value"], serial_api=e2e_fp32["serial_api"] + " (fp32 tensors)")
         out = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
-            "config": {"workload": f"MiT-{VARIANT.upper()} + CFFM head (depth {HEAD_DEPTH[VARIANT]}), {H}x{W}, T={T}, {B} clips per GPU" + (" (BASELINE configs[1])" if VARIANT == "b1" else ""),
+            "config": {"workload": f"MiT-{VARIANT.upper()} + CFFM{'++ (K=%d prototypes)' % PROTOS if KIND == 'cffmpp' else ''} head (depth {HEAD_DEPTH[VARIANT]}), {H}x{W}, T={T}, {B} clips per GPU" +
+                                   (" (BASELINE configs[1])" if (VARIANT, KIND, T, B) == ("b1", "cffm", 4, 2) else
+                                    " (BASELINE configs[0]: T != num_clips, the head's early-return path)" if (VARIANT, T, B) == ("b0", 2, 1) else
+                                    " (BASELINE configs[3])" if (VARIANT, KIND, T) == ("b2", "cffm", 4) else
+                                    " (BASELINE configs[4])" if (VARIANT, KIND, PROTOS) == ("b1", "cffmpp", 64) else ""),
                        "clips_per_gpu": B, "frames_per_step": B * T * n_gpus, "shard": args.shard if n_gpus > 1 else "none",
                        "l2": "256 MiB flush between timed steps", "timing": "per-step CUDA events, max over ranks"},
             "clocks": clocks,
-            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms / args.steps, 4),
-                    "h2d_bytes_per_step": B * T * 3 * H * W * 4, "d2h_bytes_per_step": B * H * W * 8,
-                    "api": e2e_api,
-                    "serial_value": round(frames / (e2e_serial_ms * 1e-3), 2),
-                    "serial_api": "graph.load(pinned host frames) -> replay -> D2H labels, one step at a time (no overlap)"},
-            "e2e_from_uint8_frames": (dict(e2e_u8, value=round(frames / (e2e_u8_ms * 1e-3), 2), ms_per_step=round(e2e_u8_ms / args.steps, 4))
-                                      if e2e_u8 else None),
+            "e2e": e2e_main,
+            "e2e_from_fp32_tensors": e2e_fp32 if e2e_u8 else None,
+            "e2e_mmseg_call": mmseg_call,
             "streaming": (dict(streaming, stateless_equivalent=round(value / T, 2)) if streaming else None),
             "gpu_launches": launches,
             "launch_mode": (f"CUDA graph replay ({graphed.kernels_per_replay} kernel nodes per step)" if graphed is not None else

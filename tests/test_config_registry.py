@@ -146,3 +146,31 @@ def test_modules_refuse_training_and_cpu_execution():
         m(img=None, img_metas=None, return_loss=True)
     with pytest.raises(TypeError):
         m.forward_test(torch.zeros(1), [[]])
+
+
+def test_cffmpp_load_centers_both_branches(tmp_path):
+    """``_load_centers`` (reference cffm_head.py:429-455): <save_path>/<video>/centers.pt when it exists; otherwise every
+    *.pt of the video concatenated along the prototype axis and a random 80 % of them kept, in their original order."""
+    head = V.build_head(V.model_cfg("b1", "cffmpp")["decode_head"])
+    head.save_path = str(tmp_path) + "/"
+    (tmp_path / "vidA").mkdir(); (tmp_path / "vidB").mkdir()
+    ca = torch.arange(1 * 64 * 256, dtype=torch.float32).view(1, 64, 256)
+    torch.save(ca, tmp_path / "vidA" / "centers.pt")
+    parts = [torch.full((1, 10, 256), float(i)) + torch.arange(10).view(1, 10, 1) * 0.01 for i in range(8)]   # 80 prototypes
+    for i, p in enumerate(parts):
+        torch.save(p, tmp_path / "vidB" / f"part{i:02d}.pt")
+    metas = [dict(filename="data/vidA/origin/00000001.jpg")]
+    got = head._load_centers(metas, 1, "cpu")
+    assert torch.equal(got, ca)
+    metas = [dict(filename="data/vidB/origin/00000007.jpg")]
+    torch.manual_seed(0)
+    got = head._load_centers(metas, 1, "cpu")
+    allp = torch.cat(parts, dim=1)[0]
+    assert got.shape == (1, 64, 256)                           # int(80 * 0.8) kept
+    # every kept row is one of the 80 prototypes, each at most once, original order preserved
+    idx = [int((allp == r).all(dim=1).nonzero()[0]) for r in got[0]]
+    assert idx == sorted(set(idx)) and len(idx) == 64
+    with pytest.raises(FileNotFoundError):
+        head._load_centers([dict(filename="data/vidC/origin/00000001.jpg")], 1, "cpu")
+    with pytest.raises(AssertionError):
+        head._load_centers(metas, 2, "cpu")                    # batch_size must equal len(img_metas) (:430)

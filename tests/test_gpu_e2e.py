@@ -7,8 +7,9 @@ Tolerances.  The GPU path computes with fp16 operands / fp32 accumulation and an
 stream; the reference is fp32 throughout.  north_star's bar is 1e-3 relative for the head on
 identical inputs; stacked stages accumulate independent fp16 roundings, so the bars are
   head / CFFM blocks / CFFM++ branch (identical fp16-representable inputs): 1e-3 of the output scale (the north_star bar)
-  MiT backbone, 8+ blocks deep                                            : 1e-2 of the output scale
-  end to end                                                              : 1e-2, labels >= 99 % equal
+  MiT backbone, 8+ blocks deep                                            : 2e-3 of the output scale (0.8-1.4e-3 measured)
+  end to end                                                              : 2e-3 (1.0-1.4e-3 measured), labels >= 99 % equal
+  MiT-B5 (52 blocks) end to end                                           : 4e-3
 measured as max|gpu - ref| / max|ref|; the achieved values are printed (-s) and logged in DESIGN.md."""
 import json
 import os
@@ -55,7 +56,7 @@ def test_mit_backbone_vs_reference_golden(golden_dir, tag, seed):
         assert tuple(o.shape) == g[f"out{i}"].shape
         e = rel_err(o, g[f"out{i}"])
         print(f"mit_{tag} stage {i}: rel err {e:.2e}")
-        assert e <= 1e-2, (i, e)
+        assert e <= 2e-3, (i, e)
 
 
 def test_cffm_blocks_vs_reference_golden(golden_dir):
@@ -121,7 +122,7 @@ def test_end_to_end_vs_reference_golden(golden_dir, tag, T, B, seed, depth):
     e = rel_err(logits, g["logits"])
     agree = (np.stack(pred) == g["pred"]).mean()
     print(f"e2e {tag} T={T}: logits rel err {e:.2e}, label agreement {agree:.4f}")
-    assert e <= 1e-2, e
+    assert e <= 2e-3, e
     assert agree >= 0.99, agree
 
 
@@ -241,7 +242,7 @@ def test_full_size_vs_oracle(tag, H, W, depth):
     e = rel_err(logits, ref_logits)
     agree = float((pred == ref_pred.numpy()).mean())
     print(f"full size {tag} {H}x{W}: logits rel err {e:.2e}, label agreement {agree:.4f}")
-    assert pred.shape == (1, H, W) and e <= 1e-2 and agree >= 0.99, (e, agree)
+    assert pred.shape == (1, H, W) and e <= 2e-3 and agree >= 0.99, (e, agree)
 
 
 def test_full_size_reference_frames_do_not_leak_between_clips(full_model):
@@ -339,3 +340,63 @@ def test_mixed_geometries_on_one_model_equal_fresh_models(sizes):
         got = m.predict_labels(imgs, metas).clone()
         want = build("b0", seed=43).predict_labels(imgs, metas)
         assert torch.equal(got, want), (i, H, W)
+
+
+# ------------------------------------------------------------------ round 2: production grid / B5 depth 4 / CFFM++ 60 x 60 goldens
+def test_cffm_blocks_vs_reference_golden_production_grid(golden_dir):
+    """decoder_focal (2 blocks) on the PRODUCTION grid (1,4,256,60,60) -- 81 windows, every ring / pooled border case -- vs the
+    golden of the unmodified reference's BasicLayer3d3 (target frame, every 3rd pixel)."""
+    import vss_cffm_b200 as V
+    g = np.load(os.path.join(golden_dir, "basic_layer3d3_60x60.npz"))
+    head = V.build_head(V.model_cfg("b1")["decode_head"])
+    sd = head.state_dict()
+    for k in list(sd):
+        if k.startswith("decoder_focal.") and sd[k].is_floating_point() and not synth.is_derived_buffer(k):
+            sd[k] = synth.synth_tensor(k, sd[k].shape, 4)
+    head.load_state_dict(sd)
+    head = head.cuda().eval()
+    got = _run_cffm_blocks(head, synth.synth_array((1, 4, 256, 60, 60), 23))          # (H, W, C)
+    e = rel_err(got[::3, ::3], torch.from_numpy(g["target_s3"]).permute(1, 2, 0))
+    print(f"BasicLayer3d3 depth 2 at 60x60: rel err {e:.2e}")
+    assert e <= 1e-3, e
+
+
+def test_end_to_end_mit_b5_depth4_vs_reference_golden(golden_dir):
+    """MiT-B5 + CFFM head of depth 4 (local_configs/cffm/B5/cffm.b5.480x480.vspw2.160k.py) vs the unmodified reference."""
+    g = np.load(os.path.join(golden_dir, "e2e_b5_T4.npz"))
+    m = build("b5", seed=11)
+    assert len(m.decode_head.decoder_focal.blocks) == 4
+    imgs = synth.synth_clip(1, 4, 64, 96, seed=11)
+    metas = [synth.img_metas(1, 64, 96)]
+    pred = m(img=[imgs], img_metas=metas, return_loss=False)
+    frames, _, _ = m._stack(imgs)
+    logits = m.encode_decode_frames(frames, metas[0], 1, 4)
+    e = rel_err(logits, g["logits"])
+    agree = (np.stack(pred) == g["pred"]).mean()
+    print(f"e2e b5 T=4 (52 backbone blocks, head depth 4): logits rel err {e:.2e}, label agreement {agree:.4f}")
+    assert e <= 4e-3 and agree >= 0.99, (e, agree)
+
+
+@pytest.mark.parametrize("K", [64, 100])
+def test_cffmpp_cluster_branch_production_grid(golden_dir, K):
+    """CFFM++ prototype layer on 3600 tokens (60 x 60) with K = 64 (BASELINE configs[4]) and K = 100 (README) prototypes vs the
+    unmodified reference's decoder_swin (every 9th token)."""
+    import vss_cffm_b200 as V
+    g = np.load(os.path.join(golden_dir, "cffmpp_cluster_layer_60x60.npz"))
+    head = V.build_head(V.model_cfg("b1", "cffmpp")["decode_head"])
+    sd = head.state_dict()
+    for k in list(sd):
+        if k.startswith("decoder_swin.") and sd[k].is_floating_point() and not synth.is_derived_buffer(k):
+            sd[k] = synth.synth_tensor("decode_head." + k, sd[k].shape, 9)
+    w3 = torch.zeros_like(sd["linear_pred3.weight"]); w3[:, :124, 0, 0] = torch.eye(124)
+    sd["linear_pred3.weight"], sd["linear_pred3.bias"] = w3, torch.zeros(124)
+    head.load_state_dict(sd)
+    head = head.cuda().eval()
+    P = head._build_plan()
+    tok = synth.synth_array((1, 3600, 256), 43)
+    centers = synth.synth_array((1, K, 256), 44 + K)
+    lg = torch.zeros(3600, P["ncp"], dtype=torch.float32, device="cuda")
+    head._cluster_branch(P, tok.view(3600, 256).cuda().clone(), centers.cuda(), lg, 1, 3600)
+    e = rel_err(2.0 * lg[:, :124].view(1, 3600, 124)[:, ::9], g[f"out_k{K}_s9"][:, :, :124])
+    print(f"CFFM++ cluster layer 60x60, K={K}: rel err {e:.2e}")
+    assert e <= 1e-3, e

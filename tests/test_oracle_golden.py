@@ -107,3 +107,41 @@ def test_cffmpp_cluster_layer(golden_dir):
     centers = synth.synth_array((2, 10, 256), 42)
     out = O.cluster_layer(sd, "decode_head.decoder_swin", tok, centers, 1)
     _close(out, g["out"], rtol=5e-5)
+
+
+# ------------------------------------------------------------------ round 2: production grid, MiT-B5 + depth 4, CFFM++ at 60 x 60
+def test_basic_layer3d3_production_grid(golden_dir):
+    """BasicLayer3d3 on (1,4,256,60,60): 81 windows, every ring / pooled border case, vs the unmodified reference."""
+    g = np.load(os.path.join(golden_dir, "basic_layer3d3_60x60.npz"))
+    spec = {k[len("decode_head."):]: v for k, v in _spec(golden_dir, "b1").items()
+            if k.startswith("decode_head.decoder_focal.")}
+    sd = synth.synth_state_dict(spec, 4)
+    x = synth.synth_array((1, 4, 256, 60, 60), 23)
+    y = O.basic_layer3d3(sd, "decoder_focal", x, 2)
+    assert torch.equal(y[:, :-1], x[:, :-1])
+    _close(y[0, -1, :, ::3, ::3], g["target_s3"], rtol=5e-5)
+
+
+def test_end_to_end_mit_b5_depth4(golden_dir):
+    """MiT-B5 ([3,6,40,3] blocks) + CFFM head of depth 4 (local_configs/cffm/B5) vs the unmodified reference."""
+    g = np.load(os.path.join(golden_dir, "e2e_b5_T4.npz"))
+    with open(os.path.join(golden_dir, "state_dict_spec_b5.json")) as f:
+        spec = json.load(f)["b5"]
+    assert sum(1 for k in spec if k.startswith("decode_head.decoder_focal.blocks.") and k.endswith("norm1.weight")) == 4
+    sd = synth.synth_state_dict(spec, 11)
+    imgs = synth.synth_clip(1, 4, 64, 96, seed=11)
+    pred, logits = O.segmentor_simple_test(sd, imgs, "mit_b5", 4, return_logits=True)
+    _close(logits, g["logits"], rtol=2e-4)
+    assert (pred.numpy() == g["pred"]).mean() >= 0.9995
+
+
+def test_cffmpp_cluster_layer_production_grid(golden_dir):
+    g = np.load(os.path.join(golden_dir, "cffmpp_cluster_layer_60x60.npz"))
+    spec = {k[len("decode_head."):]: v for k, v in _spec(golden_dir, "b1pp").items()
+            if k.startswith("decode_head.decoder_swin.")}
+    sd = synth.synth_state_dict({"decode_head." + k: v for k, v in spec.items()}, 9)
+    tok = synth.synth_array((1, 3600, 256), 43)
+    for K in (64, 100):
+        centers = synth.synth_array((1, K, 256), 44 + K)
+        out = O.cluster_layer(sd, "decode_head.decoder_swin", tok, centers, 1)
+        _close(out[:, ::9], g[f"out_k{K}_s9"], rtol=5e-5)
