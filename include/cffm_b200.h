@@ -94,6 +94,25 @@ int cffm_gemm_f16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw,
                          int M, int N, int K, int splits, void* stream);
 int cffm_splitk_plan(int M, int N, int K);
 
+/* Convolutions as implicit GEMMs on the same tcgen05 kernel (no im2col matrix is written): x fp16 NHWC
+ * [n, H, W, C] (C % 64 == 0), filter ksize x ksize, weights fp16 [Nout, ksize*ksize*C] in (ky, kx, c)
+ * order.  The A operand is the image itself, read through a 4-D tensor map whose boxes walk it with the
+ * convolution stride (one box per filter tap and 64-channel chunk); out-of-image taps are the TMA's zero
+ * fill = the convolution's zero padding.  Needs Wo <= 128 and Wo * stride <= 256 (one box per output
+ * row group); larger images go through cffm_im2col + cffm_gemm_f16.
+ * OverlapPatchEmbed.proj (k3 s2 p1) and Attention.sr (k = stride), mix_transformer.py:76,101-102,173-195.
+ *   _ln     : y = conv + bias -> out_f32 (optional) ; LayerNorm(y; gamma1, beta1) -> ln_out_f16; with gamma2 != NULL the
+ *             first LayerNorm's result goes to out_f32 and a second LayerNorm (gamma2, beta2) of it to ln_out_f16
+ *             (patch-embed norm + first block's norm1).  Nout <= 128.
+ *   _splitk : partials[s] = the s-th K range of the convolution, fp32 [splits, n*Ho*Wo, Nout] (summed by
+ *             cffm_layernorm_sum / cffm_layernorm_chain). */
+int cffm_conv_gemm_f16_ln(const void* x, int n, int H, int W, int C, int ksize, int stride, int pad, const void* Wt,
+                          int64_t ldw, const float* bias, float* out_f32, int64_t ldo32, const float* gamma1,
+                          const float* beta1, float eps1, const float* gamma2, const float* beta2, float eps2,
+                          void* ln_out_f16, int64_t ldln, int Nout, void* stream);
+int cffm_conv_gemm_f16_splitk(const void* x, int n, int H, int W, int C, int ksize, int stride, int pad,
+                              const void* Wt, int64_t ldw, float* partials, int Nout, int splits, void* stream);
+
 /* LayerNorm of x = sum_s partials[s] + bias (partials fp32 [nsum, M, C] contiguous; bias may be NULL):
  * the reduction of cffm_gemm_f16_splitk fused into the LayerNorm that follows every such conv
  * (mix_transformer.py:103,198). */

@@ -557,3 +557,61 @@ def test_splitk_gemm_and_summing_layernorm(ops, M, N, K):
     o32b = torch.empty_like(o32)
     ops.layernorm_sum(parts, bias, g, b, 1e-5, out32=o32b)
     assert torch.equal(o32, o32b)                                  # fixed summation order: deterministic
+
+
+# ------------------------------------------------------------------------------------ implicit-GEMM convolutions
+def _ln(x, g, b, eps):
+    return F.layer_norm(x, (x.shape[-1],), g, b, eps)
+
+
+@pytest.mark.parametrize("n,H,W,C,k,s,p,Nout,chain", [
+    (2, 24, 30, 64, 3, 2, 1, 128, True),      # OverlapPatchEmbed k3 s2 p1, both LayerNorms chained, short last tile
+    (8, 120, 120, 64, 3, 2, 1, 128, True),    # stage-2 patch embed at 480x480
+    (2, 16, 24, 128, 4, 4, 0, 128, False),    # Attention.sr, kernel = stride
+    (1, 7, 9, 64, 3, 2, 1, 64, False),        # odd sizes, one partial tile
+    (1, 60, 216, 64, 3, 2, 1, 128, True),     # 480x864 input: 108-wide output rows, one row per tile
+])
+def test_conv_gemm_ln_vs_conv2d(ops, n, H, W, C, k, s, p, Nout, chain):
+    """Implicit-GEMM convolution (TMA boxes walking the NHWC image with the conv stride, zero fill = zero padding) + bias +
+    fused LayerNorm(s) == F.conv2d + F.layer_norm in fp32 on the same fp16-representable operands."""
+    x = h16(synth.synth_array((n, H, W, C), 61))
+    w = h16(synth.synth_array((Nout, C, k, k), 62, scale=(k * k * C) ** -0.5))
+    bias = synth.synth_array((Nout,), 63)
+    g1, b1 = 1 + 0.1 * synth.synth_array((Nout,), 64), 0.1 * synth.synth_array((Nout,), 65)
+    g2, b2 = 1 + 0.1 * synth.synth_array((Nout,), 66), 0.1 * synth.synth_array((Nout,), 67)
+    y = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double(), stride=s, padding=p).permute(0, 2, 3, 1).float()
+    Ho, Wo = y.shape[1:3]
+    M = n * Ho * Wo
+    y = y.reshape(M, Nout)
+    wk = w.permute(0, 2, 3, 1).reshape(Nout, k * k * C).contiguous().cuda().half()          # (ky, kx, c) order
+    out32 = torch.full((M, Nout), float("nan"), device="cuda")
+    ln16 = torch.full((M, Nout), float("nan"), dtype=torch.float16, device="cuda")
+    cu = lambda t: t.cuda()
+    if chain:
+        ops.conv_gemm_ln(x.cuda().half(), n, H, W, C, k, s, p, wk, cu(bias), out32, cu(g1), cu(b1), 1e-5, ln16, cu(g2), cu(b2), 1e-6)
+        y1 = _ln(y, g1, b1, 1e-5)
+        check(out32, y1, REL32, "LN1(conv) fp32")
+        check(ln16, _ln(y1, g2, b2, 1e-6), REL16, "LN2(LN1(conv)) fp16")
+    else:
+        ops.conv_gemm_ln(x.cuda().half(), n, H, W, C, k, s, p, wk, cu(bias), out32, cu(g1), cu(b1), 1e-5, ln16)
+        check(out32, y, REL32, "conv fp32")
+        check(ln16, _ln(y, g1, b1, 1e-5), REL16, "LN(conv) fp16")
+    assert not torch.isnan(out32).any() and not torch.isnan(ln16.float()).any()            # every row of every (short) tile written
+
+
+@pytest.mark.parametrize("n,H,W,C,k,s,p,Nout", [
+    (8, 120, 120, 64, 8, 8, 0, 64),           # stage-1 Attention.sr at 480x480: K = 4096, 8 splits, 15-row images in 2 tiles
+    (2, 30, 30, 320, 3, 2, 1, 512),           # stage-4 patch embed: K = 2880, 5 splits
+    (1, 60, 108, 128, 4, 4, 0, 128),          # stage-2 sr of a 480x864 input
+])
+def test_conv_gemm_splitk_vs_conv2d(ops, n, H, W, C, k, s, p, Nout):
+    x = h16(synth.synth_array((n, H, W, C), 71))
+    w = h16(synth.synth_array((Nout, C, k, k), 72, scale=(k * k * C) ** -0.5))
+    y = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), None, stride=s, padding=p).permute(0, 2, 3, 1).float()
+    M = y.shape[0] * y.shape[1] * y.shape[2]
+    wk = w.permute(0, 2, 3, 1).reshape(Nout, k * k * C).contiguous().cuda().half()
+    S = ops.splitk_plan(M, Nout, k * k * C)
+    assert S > 1
+    part = torch.full((S, M, Nout), float("nan"), device="cuda")
+    ops.conv_gemm_splitk(x.cuda().half(), n, H, W, C, k, s, p, wk, part)
+    check(part.sum(0), y.reshape(M, Nout), REL32, "sum of split-K partials")

@@ -53,7 +53,29 @@ struct Epilogue {
   int splits;
   int kb_per;
   int64_t split_stride;
+  // Implicit-GEMM convolution (0 = plain GEMM): A is an NHWC fp16 image read through a 4-D tensor map whose boxes walk the
+  // image with the convolution stride (cuTensorMap elementStrides), one box per (filter tap, 64-channel chunk) and M tile.
+  // An M tile is conv_by full output rows (conv_by * Wo <= 128 rows of the GEMM) of ONE image; out-of-image taps are the TMA's
+  // zero fill, i.e. the convolution's zero padding.  The rows of a tile are contiguous in M, but a tile starts at
+  // image * Ho * Wo + tile_y * conv_by * Wo instead of a multiple of 128, and the last tile of an image is short.
+  int conv_k;                // filter size (k x k), 0 = plain GEMM
+  int conv_stride, conv_pad;
+  int conv_cchunks;          // C / 64
+  int conv_Wo, conv_Ho, conv_by, conv_tiles_y;
 };
+
+// First row and number of valid rows of M tile `mt`
+__device__ __forceinline__ void tile_rows(const Epilogue& ep, int mt, int M, int& m0, int& mrows) {
+  if (ep.conv_k == 0) {
+    m0 = mt * 128;
+    mrows = min(128, M - m0);
+  } else {
+    const int img = mt / ep.conv_tiles_y, ty = mt - img * ep.conv_tiles_y;
+    const int per = ep.conv_by * ep.conv_Wo, grp = ep.conv_Ho * ep.conv_Wo;
+    m0 = img * grp + ty * per;
+    mrows = min(per, grp - ty * per);
+  }
+}
 
 // EW = number of epilogue warps.  16: one CTA per SM, the throughput configuration (big GEMMs).  8 (BN = 64 only): a CTA
 // of 10 warps and <= 112 KB of shared memory, so TWO CTAs share an SM -- the latency configuration for the GEMMs with few
@@ -147,14 +169,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t g = 0;                                            // k-blocks issued so far (all tiles)
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int split = t % ep.splits, tt = t / ep.splits;
-      const int m0 = (tt / n_tiles_n) * BLOCK_M, n0 = (tt % n_tiles_n) * BN;
+      const int mt = tt / n_tiles_n, n0 = (tt % n_tiles_n) * BN;
       const int kb0 = split * ep.kb_per, kb1 = min(num_kb, kb0 + ep.kb_per);
+      const int img = ep.conv_k ? mt / ep.conv_tiles_y : 0;
+      const int y0 = ep.conv_k ? (mt - img * ep.conv_tiles_y) * ep.conv_by * ep.conv_stride - ep.conv_pad : 0;
       for (int kb = kb0; kb < kb1; ++kb, ++g) {
         const uint32_t s = g % C::STAGES, ph = (g / C::STAGES) & 1u;
         ptx::mbar_wait(&empty_bar[s], ph ^ 1u);                // slot free (passes on the first round)
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-          ptx::tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BLOCK_K, m0);
+          if (ep.conv_k == 0) {
+            ptx::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+            ptx::tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BLOCK_K, mt * BLOCK_M);
+          } else {
+            const int tap = kb / ep.conv_cchunks, c0 = (kb - tap * ep.conv_cchunks) * BLOCK_K;
+            const int ky = tap / ep.conv_k, kx = tap - ky * ep.conv_k;
+            ptx::mbar_arrive_expect_tx(&full_bar[s], ep.conv_by * ep.conv_Wo * BLOCK_K * 2 + C::W_STAGE_BYTES);
+            ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], c0, kx - ep.conv_pad, y0 + ky, img);
+          }
           ptx::tma_load_2d(sW + s * C::W_STAGE_BYTES, &tmW, &full_bar[s], kb * BLOCK_K, n0);
         }
         __syncwarp();
@@ -206,7 +237,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t it = tm;
     for (int t = blockIdx.x + tm * static_cast<int>(gridDim.x); t < n_tiles; t += tstep, it += C::TEAMS) {
       const int split = t % ep.splits, tt = t / ep.splits;
-      const int m0 = (tt / n_tiles_n) * BLOCK_M, n0 = (tt % n_tiles_n) * BN;
+      const int n0 = (tt % n_tiles_n) * BN;
+      int m0, mrows;
+      tile_rows(ep, tt / n_tiles_n, M, m0, mrows);
+      const int mend = m0 + mrows;                             // rows [m0, mend) of the output belong to this tile
       const int wcol0 = n0 + cg * 32;                          // first column of this warp
       const int wrow0 = m0 + wq * 32;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
@@ -250,7 +284,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         ptx::fence_proxy_async();                              // generic-proxy writes -> visible to the TMA (async proxy)
         __syncwarp();
-        if (lane == 0 && wcol0 < N && wrow0 < M) {
+        if (lane == 0 && wcol0 < N && wrow0 < mend) {
           ptx::tma_store_2d(&tmO, stg8, wcol0, wrow0);
           ptx::bulk_commit();
         }
@@ -265,7 +299,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = wrow0 + rsub + 4 * i;
-          r4[i] = (row < M && cvalid) ? *reinterpret_cast<const float4*>(ep.residual + static_cast<int64_t>(row) * ep.ldr + col)
+          r4[i] = (row < mend && cvalid) ? *reinterpret_cast<const float4*>(ep.residual + static_cast<int64_t>(row) * ep.ldr + col)
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
@@ -295,7 +329,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (ep.residual != nullptr) { a.x += r4[i].x; a.y += r4[i].y; a.z += r4[i].z; a.w += r4[i].w; }
         av[i] = a;
-        if (row < M && cvalid) {
+        if (row < mend && cvalid) {
           if (ep.out32 != nullptr && LN != 2)
             *reinterpret_cast<float4*>(ep.out32 + split * ep.split_stride + static_cast<int64_t>(row) * ep.ldo32 + col) = a;
           if (ep.out16 != nullptr) {
@@ -375,7 +409,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float rs = row_rstd(i, ep.ln_eps);
             av[i].x = (av[i].x - mean[i]) * rs * g4.x + be4.x; av[i].y = (av[i].y - mean[i]) * rs * g4.y + be4.y;
             av[i].z = (av[i].z - mean[i]) * rs * g4.z + be4.z; av[i].w = (av[i].w - mean[i]) * rs * g4.w + be4.w;
-            if (row < M && cvalid && ep.out32 != nullptr)
+            if (row < mend && cvalid && ep.out32 != nullptr)
               *reinterpret_cast<float4*>(ep.out32 + static_cast<int64_t>(row) * ep.ldo32 + col) = av[i];
           }
           asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NG * 32) : "memory");   // everyone has read bsq of the first norm
@@ -394,7 +428,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint2 h;
             h.x = pack_half2((av[i].x - mean[i]) * rs * g4.x + be4.x, (av[i].y - mean[i]) * rs * g4.y + be4.y);
             h.y = pack_half2((av[i].z - mean[i]) * rs * g4.z + be4.z, (av[i].w - mean[i]) * rs * g4.w + be4.w);
-            if (row < M) *reinterpret_cast<uint2*>(ep.ln_out16 + static_cast<int64_t>(row) * ep.ldln + col) = h;
+            if (row < mend) *reinterpret_cast<uint2*>(ep.ln_out16 + static_cast<int64_t>(row) * ep.ldln + col) = h;
           }
         }
       }
@@ -519,6 +553,48 @@ int make_tmap_4d(CUtensorMap* tm, const void* base, const int64_t dims[4], const
   return make_tmap_nd(tm, base, 4, dims, strides, box);
 }
 
+// Convolution operand: NHWC fp16 image [n, H, W, C] walked with the convolution stride.  Box = 64 channels x Wo output
+// columns x by output rows of one image: boxDim = N * elementStride loads N elements (cuda.h, cuTensorMapEncodeTiled).
+struct ConvDesc {
+  const void* x;
+  int n, H, W, C, k, stride, pad;
+  int Ho, Wo, by, tiles_y;
+};
+
+static int conv_desc(ConvDesc* cv, const void* x, int n, int H, int W, int C, int k, int stride, int pad) {
+  CFFM_REQUIRE(x && n > 0 && H > 0 && W > 0 && k >= 1 && stride >= 1 && stride <= 8 && pad >= 0 && pad < k, CFFM_E_BADARG,
+               "conv_gemm: bad geometry n=%d H=%d W=%d k=%d stride=%d pad=%d", n, H, W, k, stride, pad);
+  CFFM_REQUIRE(C % 64 == 0, CFFM_E_UNSUPPORTED, "conv_gemm: input channels must be a multiple of 64 (one k-block = one tap x 64 channels), got %d", C);
+  CFFM_REQUIRE(aligned16(x), CFFM_E_BADARG, "conv_gemm: misaligned image");
+  cv->x = x; cv->n = n; cv->H = H; cv->W = W; cv->C = C; cv->k = k; cv->stride = stride; cv->pad = pad;
+  cv->Ho = (H + 2 * pad - k) / stride + 1;
+  cv->Wo = (W + 2 * pad - k) / stride + 1;
+  CFFM_REQUIRE(cv->Wo <= 128 && cv->Wo * stride <= 256, CFFM_E_UNSUPPORTED,
+               "conv_gemm: output width %d (x stride %d) exceeds one TMA box; use cffm_im2col + cffm_gemm_f16 for this size", cv->Wo, stride);
+  int by = 128 / cv->Wo;
+  if (by * stride > 256) by = 256 / stride;
+  if (by > cv->Ho) by = cv->Ho;
+  cv->by = by;
+  cv->tiles_y = (cv->Ho + by - 1) / by;
+  return CFFM_OK;
+}
+
+static int make_tmap_conv(CUtensorMap* tm, const ConvDesc& cv) {
+  EncodeTiledFn fn = get_encode_fn();
+  CFFM_REQUIRE(fn != nullptr, CFFM_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cv.C), static_cast<cuuint64_t>(cv.W), static_cast<cuuint64_t>(cv.H), static_cast<cuuint64_t>(cv.n)};
+  cuuint64_t gstride[3] = {static_cast<cuuint64_t>(cv.C) * 2, static_cast<cuuint64_t>(cv.W) * cv.C * 2,
+                           static_cast<cuuint64_t>(cv.H) * cv.W * cv.C * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(cv.Wo * cv.stride), static_cast<cuuint32_t>(cv.by * cv.stride), 1};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(cv.stride), static_cast<cuuint32_t>(cv.stride), 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(cv.x), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CFFM_REQUIRE(r == CUDA_SUCCESS, CFFM_E_DRIVER, "cuTensorMapEncodeTiled (conv) failed with CUresult %d (C=%d W=%d H=%d n=%d, box %u %u %u)",
+               static_cast<int>(r), cv.C, cv.W, cv.H, cv.n, box[0], box[1], box[2]);
+  return CFFM_OK;
+}
+
 // fp16 [rows, cols] output (row stride ld elements) as the target of per-warp 32 x 32 bulk stores (64-byte swizzle).
 static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld) {
   EncodeTiledFn fn = get_encode_fn();
@@ -538,11 +614,20 @@ static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_
 namespace {
 
 template <int BN, bool F16_ONLY, int LN = 0, int EW = 16>
-int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const Epilogue& ep, int M, int N, int K,
-                   cudaStream_t st) {
+int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const Epilogue& ep_in, int M, int N, int K,
+                   cudaStream_t st, const ConvDesc* cv = nullptr) {
   using C = Cfg<BN, EW, F16_ONLY>;
   CUtensorMap tmA, tmW;
-  int rc = make_tmap(&tmA, A, M, K, lda, BLOCK_M);
+  Epilogue ep = ep_in;
+  int rc;
+  if (cv != nullptr) {                                         // implicit-GEMM convolution: A = the image itself
+    CFFM_REQUIRE(!F16_ONLY, CFFM_E_UNSUPPORTED, "conv_gemm: the bulk-store epilogue needs 128-row aligned tiles");
+    ep.conv_k = cv->k; ep.conv_stride = cv->stride; ep.conv_pad = cv->pad; ep.conv_cchunks = cv->C / BLOCK_K;
+    ep.conv_Wo = cv->Wo; ep.conv_Ho = cv->Ho; ep.conv_by = cv->by; ep.conv_tiles_y = cv->tiles_y;
+    rc = make_tmap_conv(&tmA, *cv);
+  } else {
+    rc = make_tmap(&tmA, A, M, K, lda, BLOCK_M);
+  }
   if (rc) return rc;
   rc = make_tmap(&tmW, W, N, K, ldw, BN);
   if (rc) return rc;
@@ -558,7 +643,7 @@ int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const
                                     C::SMEM_BYTES);
   });
   CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = cv != nullptr ? cv->n * cv->tiles_y : (M + BLOCK_M - 1) / BLOCK_M;
   const int tiles = tiles_n * tiles_m * ep.splits;
   const int slots = num_sms() * C::MIN_CTAS;
   const int grid = tiles < slots ? tiles : slots;
@@ -697,4 +782,57 @@ extern "C" int cffm_splitk_plan(int M, int N, int K) {
   if (s < 1) s = 1;
   const int kb_per = (num_kb + s - 1) / s;
   return (num_kb + kb_per - 1) / kb_per;                       // no empty split
+}
+
+// ------------------------------------------------------------------------------------------------
+// Convolutions as implicit GEMMs: no im2col matrix is ever written.
+extern "C" int cffm_conv_gemm_f16_ln(const void* x, int n, int H, int W, int C, int ksize, int stride, int pad, const void* Wt,
+                                     int64_t ldw, const float* bias, float* out_f32, int64_t ldo32, const float* gamma1,
+                                     const float* beta1, float eps1, const float* gamma2, const float* beta2, float eps2,
+                                     void* ln_out_f16, int64_t ldln, int Nout, void* stream) {
+  using namespace cffm;
+  ConvDesc cv;
+  int rc = conv_desc(&cv, x, n, H, W, C, ksize, stride, pad);
+  if (rc) return rc;
+  const int M = n * cv.Ho * cv.Wo, K = ksize * ksize * C;
+  CFFM_REQUIRE(Wt && gamma1 && beta1 && ln_out_f16, CFFM_E_BADARG, "conv_gemm_ln: null operand");
+  CFFM_REQUIRE(Nout > 0 && Nout <= 128 && Nout % 8 == 0, CFFM_E_UNSUPPORTED,
+               "conv_gemm_ln: the fused LayerNorm needs the whole row in one tile (N <= 128, multiple of 8), got N=%d", Nout);
+  CFFM_REQUIRE(ldw % 8 == 0 && ldw >= K, CFFM_E_UNSUPPORTED, "conv_gemm_ln: bad weight stride %lld for K=%d", (long long)ldw, K);
+  CFFM_REQUIRE(aligned16(Wt) && aligned16(bias) && aligned16(out_f32) && aligned16(gamma1) && aligned16(beta1) && aligned16(gamma2) &&
+                   aligned16(beta2) && (reinterpret_cast<uintptr_t>(ln_out_f16) & 7) == 0,
+               CFFM_E_BADARG, "conv_gemm_ln: misaligned pointer");
+  CFFM_REQUIRE((!out_f32 || (ldo32 % 4 == 0 && ldo32 >= Nout)) && ldln % 4 == 0 && ldln >= Nout && (!gamma2 || (beta2 && out_f32)),
+               CFFM_E_BADARG, "conv_gemm_ln: bad output stride / chained LayerNorm operands");
+  Epilogue ep{bias, nullptr, 0, nullptr, 0, out_f32, ldo32, CFFM_ACT_NONE, gamma1, beta1, eps1,
+              static_cast<__half*>(ln_out_f16), ldln, gamma2, beta2, eps2, 1, (K + BLOCK_K - 1) / BLOCK_K, 0};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gamma2 != nullptr)
+    return Nout > 64 ? launch_tcgen05<128, false, 2>(nullptr, 0, Wt, ldw, ep, M, Nout, K, st, &cv)
+                     : launch_tcgen05<64, false, 2>(nullptr, 0, Wt, ldw, ep, M, Nout, K, st, &cv);
+  return Nout > 64 ? launch_tcgen05<128, false, 1>(nullptr, 0, Wt, ldw, ep, M, Nout, K, st, &cv)
+                   : launch_tcgen05<64, false, 1>(nullptr, 0, Wt, ldw, ep, M, Nout, K, st, &cv);
+}
+
+extern "C" int cffm_conv_gemm_f16_splitk(const void* x, int n, int H, int W, int C, int ksize, int stride, int pad, const void* Wt,
+                                         int64_t ldw, float* partials, int Nout, int splits, void* stream) {
+  using namespace cffm;
+  ConvDesc cv;
+  int rc = conv_desc(&cv, x, n, H, W, C, ksize, stride, pad);
+  if (rc) return rc;
+  const int M = n * cv.Ho * cv.Wo, K = ksize * ksize * C;
+  CFFM_REQUIRE(Wt && partials && Nout > 0 && Nout % 8 == 0 && splits >= 1, CFFM_E_BADARG, "conv_gemm_splitk: bad operand");
+  CFFM_REQUIRE(ldw % 8 == 0 && ldw >= K && aligned16(Wt) && aligned16(partials), CFFM_E_BADARG, "conv_gemm_splitk: bad weight stride / alignment");
+  const int num_kb = K / BLOCK_K;
+  CFFM_REQUIRE(splits <= num_kb, CFFM_E_BADARG, "conv_gemm_splitk: %d splits for %d k-blocks", splits, num_kb);
+  const int kb_per = (num_kb + splits - 1) / splits;
+  CFFM_REQUIRE((splits - 1) * kb_per < num_kb, CFFM_E_BADARG, "conv_gemm_splitk: empty split (use cffm_splitk_plan)");
+  Epilogue ep{nullptr, nullptr, 0, nullptr, 0, partials, Nout, CFFM_ACT_NONE, nullptr, nullptr, 0.f, nullptr, 0, nullptr, nullptr, 0.f,
+              splits, kb_per, static_cast<int64_t>(M) * Nout};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int tiles64 = cv.n * cv.tiles_y * ((Nout + 63) / 64) * splits;
+  if (tiles64 <= small_gemm_max_tiles()) return launch_tcgen05<64, false, 0, 8>(nullptr, 0, Wt, ldw, ep, M, Nout, K, st, &cv);
+  const bool wide = Nout % 128 == 0 || (Nout % 64 != 0 && Nout > 64);
+  return wide ? launch_tcgen05<128, false>(nullptr, 0, Wt, ldw, ep, M, Nout, K, st, &cv)
+              : launch_tcgen05<64, false>(nullptr, 0, Wt, ldw, ep, M, Nout, K, st, &cv);
 }

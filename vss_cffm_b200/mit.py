@@ -197,19 +197,31 @@ class MixVisionTransformer(nn.Module):
             k, stride, pad, C = st["k"], st["stride"], st["pad"], st["cout"]
             Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
             M = N * Ho * Wo
-            col = ws.get(f"s{s}.col", (M, st["kpad"]), _H)
-            ops.im2col(cur, layout, N, H, W, st["cin"], k, stride, pad, col)
             xres = ws.get(f"s{s}.x", (M, C), _F)                 # fp32 residual stream
             S = ops.splitk_plan(M, C, st["kpad"])                # few tiles x long K (stages 3-4): split K over the SMs
             pe32 = ws.get(f"s{s}.pe32", (S, M, C), _F)
             xn = ws.get(f"s{s}.xn", (M, C), _H)
             b0 = st["blocks"][0]
+            # The convolution is an implicit GEMM on the NHWC image itself (TMA boxes walking it with the conv stride, zero
+            # fill = zero padding) whenever the image is fp16 NHWC with C % 64 == 0 (stages 2-4); the fp32 NCHW input frames
+            # of stage 1 (3 channels) go through a patch matrix.
+            implicit = layout == 1 and ops.conv_gemm_supported(st["cin"], Wo, stride) and (S > 1 or C <= 128)
+            if not implicit:
+                col = ws.get(f"s{s}.col", (M, st["kpad"]), _H)
+                ops.im2col(cur, layout, N, H, W, st["cin"], k, stride, pad, col)
             # patch-embed norm and the first block's norm1 in one pass (the row stays in registers in between)
             if S > 1:
-                ops.gemm_splitk(col, st["w"], pe32)
+                if implicit:
+                    ops.conv_gemm_splitk(cur, N, H, W, st["cin"], k, stride, pad, st["w"], pe32)
+                else:
+                    ops.gemm_splitk(col, st["w"], pe32)
                 ops.layernorm_chain(pe32, st["b"], st["ng"], st["nb"], st["eps"], xres, b0["n1g"], b0["n1b"], b0["n1eps"], xn)
             elif C <= 128:                                       # both norms ride in the GEMM epilogue (one tile spans the row)
-                ops.gemm_ln_chain(col, st["w"], st["b"], xres, st["ng"], st["nb"], st["eps"], b0["n1g"], b0["n1b"], b0["n1eps"], xn)
+                if implicit:
+                    ops.conv_gemm_ln(cur, N, H, W, st["cin"], k, stride, pad, st["w"], st["b"], xres, st["ng"], st["nb"], st["eps"], xn,
+                                     b0["n1g"], b0["n1b"], b0["n1eps"])
+                else:
+                    ops.gemm_ln_chain(col, st["w"], st["b"], xres, st["ng"], st["nb"], st["eps"], b0["n1g"], b0["n1b"], b0["n1eps"], xn)
             else:
                 ops.gemm(col, st["w"], bias=st["b"], out32=pe32[0])
                 ops.layernorm_chain(pe32, None, st["ng"], st["nb"], st["eps"], xres, b0["n1g"], b0["n1b"], b0["n1eps"], xn)
@@ -228,14 +240,22 @@ class MixVisionTransformer(nn.Module):
                     if sr > 1:
                         Hs, Ws_ = (Ho - sr) // sr + 1, (Wo - sr) // sr + 1
                         Ms = N * Hs * Ws_
-                        scol = ws.get(f"s{s}.srcol", (Ms, sr * sr * C), _H)
-                        ops.im2col(xn, 1, N, Ho, Wo, C, sr, sr, 0, scol)
                         S = ops.splitk_plan(Ms, C, sr * sr * C)   # 15 tiles x K up to 4096: split K over the SMs
                         s32 = ws.get(f"s{s}.sr32", (S, Ms, C), _F)
                         kvin = ws.get(f"s{s}.srn", (Ms, C), _H)
+                        # Attention.sr has kernel = stride: a pure re-tiling of xn, read in place by strided TMA boxes
+                        implicit = ops.conv_gemm_supported(C, Ws_, sr) and (S > 1 or C <= 128)
+                        if not implicit:
+                            scol = ws.get(f"s{s}.srcol", (Ms, sr * sr * C), _H)
+                            ops.im2col(xn, 1, N, Ho, Wo, C, sr, sr, 0, scol)
                         if S > 1:
-                            ops.gemm_splitk(scol, b["srw"], s32)
+                            if implicit:
+                                ops.conv_gemm_splitk(xn, N, Ho, Wo, C, sr, sr, 0, b["srw"], s32)
+                            else:
+                                ops.gemm_splitk(scol, b["srw"], s32)
                             ops.layernorm_sum(s32, b["srb"], b["sng"], b["snb"], b["seps"], out16=kvin)
+                        elif implicit:                           # conv + bias + Attention.norm in one launch
+                            ops.conv_gemm_ln(xn, N, Ho, Wo, C, sr, sr, 0, b["srw"], b["srb"], None, b["sng"], b["snb"], b["seps"], kvin)
                         else:
                             ops.gemm(scol, b["srw"], bias=b["srb"], out32=s32[0])
                             ops.layernorm(s32[0], b["sng"], b["snb"], b["seps"], out16=kvin)

@@ -101,6 +101,39 @@ def gemm_splitk(a, w, partials):
     _abi.call("cffm_gemm_f16_splitk", _ptr(a), _ld(a), _ptr(w), _ld(w), _ptr(partials), M, N, K, partials.shape[0], _stream())
 
 
+def conv_gemm_supported(C, Wo, stride):
+    """The implicit-GEMM convolution takes NHWC images with C % 64 == 0 whose output rows fit one TMA box."""
+    return C % 64 == 0 and Wo <= 128 and Wo * stride <= 256
+
+
+def conv_gemm_ln(x, n, H, W, C, k, stride, pad, w, bias, out32, g1, b1, eps1, ln_out16, g2=None, b2=None, eps2=0.0):
+    """y = conv(x) + bias; LayerNorm(y) -> ln_out16 (y -> out32 when given); with g2: out32 = LN1(y), ln_out16 = LN2(out32).
+    x fp16 NHWC [n,H,W,C] (any contiguous tensor with n*H*W*C elements), w fp16 [Nout, k*k*C] in (ky,kx,c) order."""
+    _chk(x, _H, "conv_gemm_ln.x"); _chk(w, _H, "conv_gemm_ln.w"); _chk(ln_out16, _H, "conv_gemm_ln.ln_out16")
+    assert x.is_contiguous() and x.numel() == n * H * W * C and w.shape[1] >= k * k * C
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    Nout = w.shape[0]
+    assert tuple(ln_out16.shape) == (n * Ho * Wo, Nout)
+    for t in (bias, out32, g1, b1, g2, b2):
+        if t is not None:
+            _chk(t, _F, "conv_gemm_ln.f32 operand")
+    if out32 is not None:
+        assert tuple(out32.shape) == (n * Ho * Wo, Nout)
+    _abi.call("cffm_conv_gemm_f16_ln", _ptr(x), n, H, W, C, k, stride, pad, _ptr(w), _ld(w), _ptr(bias), _ptr(out32),
+              _ld(out32) if out32 is not None else 0, _ptr(g1), _ptr(b1), float(eps1), _ptr(g2), _ptr(b2), float(eps2),
+              _ptr(ln_out16), _ld(ln_out16), Nout, _stream())
+
+
+def conv_gemm_splitk(x, n, H, W, C, k, stride, pad, w, partials):
+    """partials[s] = the s-th K range of conv(x); partials fp32 [S, n*Ho*Wo, Nout] contiguous."""
+    _chk(x, _H, "conv_gemm_splitk.x"); _chk(w, _H, "conv_gemm_splitk.w"); _chk(partials, _F, "conv_gemm_splitk.partials")
+    assert x.is_contiguous() and x.numel() == n * H * W * C and w.shape[1] >= k * k * C and partials.is_contiguous()
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    assert tuple(partials.shape[1:]) == (n * Ho * Wo, w.shape[0])
+    _abi.call("cffm_conv_gemm_f16_splitk", _ptr(x), n, H, W, C, k, stride, pad, _ptr(w), _ld(w), _ptr(partials), w.shape[0],
+              partials.shape[0], _stream())
+
+
 def layernorm_sum(partials, bias, gamma, beta, eps, out16=None, out32=None):
     """LayerNorm(sum_s partials[s] + bias)."""
     _chk(partials, _F, "layernorm_sum.partials")
