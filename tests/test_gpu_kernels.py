@@ -171,7 +171,13 @@ def test_dwconv3x3_gelu(ops, N, H, W, C):
 
 @pytest.mark.parametrize("B,Nq,Nkv,heads,d", [(2, 384, 6, 1, 64), (2, 96, 6, 2, 64), (3, 200, 225, 5, 64),
                                               (2, 225, 225, 8, 64), (2, 100, 10, 8, 32), (1, 3600, 64, 8, 32),
-                                              (2, 130, 100, 1, 32)])
+                                              (2, 130, 100, 1, 32),
+                                              # tcgen05 kernel: many query tiles per resident K/V, key blocks (N_kv > 256:
+                                              # four S rounds per tile), head pairs (head_dim 32), odd head counts, tails
+                                              (2, 3000, 225, 1, 64), (3, 700, 225, 2, 64), (1, 900, 405, 5, 64),
+                                              (2, 300, 512, 2, 64), (1, 257, 257, 1, 64), (2, 150, 320, 3, 64),
+                                              (2, 1000, 225, 2, 32), (1, 500, 225, 5, 32), (2, 225, 405, 8, 32),
+                                              (1, 2000, 225, 1, 32), (1, 129, 512, 1, 32), (3, 65, 129, 3, 32)])
 def test_mha_small_kv(ops, B, Nq, Nkv, heads, d):
     C = heads * d
     q = h16(synth.synth_array((B, Nq, C), 15))

@@ -158,7 +158,7 @@ int set_smem_attr() {
 
 namespace cffm {
 int mha_tcgen05_launch(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out, int64_t ldo,
-                       int batch, int Nq, int Nkv, int heads, float scale, cudaStream_t st);
+                       int batch, int Nq, int Nkv, int heads, int head_dim, float scale, cudaStream_t st, long long* prof = nullptr);
 static bool mha_legacy() {
   static const bool on = [] { const char* e = getenv("CFFM_MHA_LEGACY"); return e && e[0] == '1'; }();
   return on;
@@ -180,8 +180,8 @@ extern "C" int cffm_mha_f16(const void* q, int64_t ldq, const void* k, const voi
   const int smem = 2 * nkv_pad * (head_dim + 8) * 2;
   CFFM_REQUIRE(smem <= 200 * 1024, CFFM_E_UNSUPPORTED, "mha: Nkv=%d does not fit in shared memory", Nkv);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (head_dim == 64 && !mha_legacy()) {                       // tcgen05 path (mha_sm100.cu); falls through when unsupported
-    const int rc5 = mha_tcgen05_launch(q, ldq, k, v, ldkv, out, ldo, batch, Nq, Nkv, heads, scale, st);
+  if (!mha_legacy()) {                                         // tcgen05 path (mha_sm100.cu); falls through when unsupported
+    const int rc5 = mha_tcgen05_launch(q, ldq, k, v, ldkv, out, ldo, batch, Nq, Nkv, heads, head_dim, scale, st);
     if (rc5 != CFFM_E_UNSUPPORTED) return rc5;
   }
   // enough CTAs for ~2 per SM; each loops over query tiles so that the K/V staging is amortised
