@@ -474,12 +474,15 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        # DRAM bytes per launch measured by ncu for the same workload (profiles/r01_traffic.json, written by tools/ncu_traffic.py
+        # DRAM bytes per launch measured by ncu for the same workload (profiles/r02_traffic.json, written by tools/ncu_traffic.py
         # from a committed capture; null when the file is missing)
-        try:
-            traffic = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")))
-        except Exception:
-            traffic = None
+        traffic = None
+        for tf in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                traffic = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", tf)))
+                break
+            except Exception:
+                continue
 
         def ncu_traffic(family):
             f = (traffic or {}).get("families", {}).get(family)

@@ -113,6 +113,19 @@ int cffm_conv_gemm_f16_ln(const void* x, int n, int H, int W, int C, int ksize, 
 int cffm_conv_gemm_f16_splitk(const void* x, int n, int H, int W, int C, int ksize, int stride, int pad,
                               const void* Wt, int64_t ldw, float* partials, int Nout, int splits, void* stream);
 
+/* Mix-FFN tail in ONE kernel: x_out = residual + fc2(GELU(dwconv3x3(hidden) + dw_b)) + b2, and optionally
+ * LayerNorm(x_out; gamma, beta, eps) -> ln_out_f16.  Replaces Mlp.dwconv + act + fc2 (mix_transformer.py:52-58, DWConv
+ * :361-368), the residual add and the next norm (Block.forward :84-88): the convolved / activated hidden map stays on chip.
+ *   hidden fp16 [n, H, W, HD] (NHWC) = fc1 output incl. bias; dw_w fp16 [9, HD] (tap-major: ky*3+kx), dw_b fp32 [HD];
+ *   W2 fp16 [N, HD] (row stride ldw2), b2 fp32 [N]; residual fp32 [n*H*W, N]; out_f32 fp32 [n*H*W, N] or NULL (may
+ *   alias residual); ln_out_f16 fp16 [n*H*W, N] or NULL (then gamma / beta are ignored).
+ * cffm_mixffn_tail_supported(N, HD) != 0 names the shapes it is built for (N in {64, 128}, HD % 64 == 0, HD <= 512);
+ * other shapes: cffm_dwconv3x3_gelu + cffm_gemm_f16(_ln). */
+int cffm_mixffn_tail_supported(int N, int HD);
+int cffm_mixffn_tail(const void* hidden, int n, int H, int W, int HD, const void* dw_w, const float* dw_b, const void* W2,
+                     int64_t ldw2, const float* b2, const float* residual, float* out_f32, const float* ln_gamma,
+                     const float* ln_beta, float ln_eps, void* ln_out_f16, int N, void* stream);
+
 /* LayerNorm of x = sum_s partials[s] + bias (partials fp32 [nsum, M, C] contiguous; bias may be NULL):
  * the reduction of cffm_gemm_f16_splitk fused into the LayerNorm that follows every such conv
  * (mix_transformer.py:103,198). */

@@ -169,6 +169,33 @@ def test_dwconv3x3_gelu(ops, N, H, W, C):
     check(out, ref, REL16, "dwconv+gelu")
 
 
+@pytest.mark.parametrize("n,H,W,HD,N,ln,alias", [(2, 16, 24, 256, 64, True, True), (1, 7, 5, 128, 64, False, True),
+                                                 (3, 30, 33, 512, 128, True, True), (2, 120, 120, 256, 64, True, False),
+                                                 (1, 9, 70, 256, 128, True, False), (2, 60, 60, 512, 128, False, True)])
+def test_mixffn_tail(ops, n, H, W, HD, N, ln, alias):
+    """x + fc2(GELU(dwconv(h))) (+ LayerNorm) in one kernel == the fp64 composition (mix_transformer.py:52-58, :84-88)."""
+    assert ops.mixffn_tail_supported(N, HD) and not ops.mixffn_tail_supported(320, 1280)
+    M = n * H * W
+    h = h16(synth.synth_array((n, HD, H, W), 61))
+    dw = h16(synth.synth_array((HD, 1, 3, 3), 62, scale=0.3))
+    dwb = synth.synth_array((HD,), 63, scale=0.1)
+    w2 = h16(synth.synth_array((N, HD), 64, scale=HD ** -0.5))
+    b2 = synth.synth_array((N,), 65, scale=0.1)
+    res = synth.synth_array((M, N), 66)
+    g, be = 1 + synth.synth_array((N,), 67, scale=0.1), synth.synth_array((N,), 68, scale=0.1)
+    act = F.gelu(F.conv2d(h.double(), dw.double(), dwb.double(), padding=1, groups=HD)).permute(0, 2, 3, 1).reshape(M, HD)
+    act = act.half().double()                                   # the kernel rounds the activated map to fp16 (the MMA operand)
+    x_ref = res.double() + act @ w2.double().t() + b2.double()
+    res_d = res.cuda().float().contiguous()
+    out32 = res_d if alias else torch.empty_like(res_d)
+    lnout = torch.empty(M, N, dtype=torch.float16, device="cuda") if ln else None
+    ops.mixffn_tail(h.permute(0, 2, 3, 1).reshape(M, HD).contiguous().cuda().half(), n, H, W, dw.view(HD, 9).t().contiguous().cuda().half(),
+                    dwb.cuda(), w2.cuda().half(), b2.cuda(), res_d, out32, g.cuda() if ln else None, be.cuda() if ln else None, 1e-6, lnout)
+    check(out32, x_ref, 1e-3, "mixffn_tail x")
+    if ln:
+        check(lnout, F.layer_norm(x_ref, (N,), g.double(), be.double(), 1e-6), REL16, "mixffn_tail LayerNorm")
+
+
 @pytest.mark.parametrize("B,Nq,Nkv,heads,d", [(2, 384, 6, 1, 64), (2, 96, 6, 2, 64), (3, 200, 225, 5, 64),
                                               (2, 225, 225, 8, 64), (2, 100, 10, 8, 32), (1, 3600, 64, 8, 32),
                                               (2, 130, 100, 1, 32),

@@ -1,5 +1,5 @@
 """Launch ONE hot kernel of the path a few times on production shapes (B=2 clips, T=4, 480x480, MiT-B1), for
-`ncu --set full -s 2 -c 1`.  usage: python tools/one_kernel.py <gemm_fc1|gemm_fc2|gemm_q|dwconv|head_fuse|argmax|mha|cfm|ln>"""
+`ncu --set full -s 2 -c 1`.  usage: python tools/one_kernel.py <gemm_fc1|gemm_fc2|gemm_q|dwconv|ffn|ffn_s2|head_fuse|argmax|mha|cfm|ln>"""
 import os
 import sys
 
@@ -28,6 +28,12 @@ elif which == "dwconv":
     N, H, W, C = 8, 120, 120, 256
     x, w, b, out = rn(N, H, W, C).half(), (rn(9, C) * 0.3).half(), rn(C), torch.empty(N, H, W, C, device="cuda", dtype=torch.half)
     fn = lambda: ops.dwconv3x3_gelu(x, w, b, out, N, H, W, C)
+elif which in ("ffn", "ffn_s2"):
+    N, H, W, C, Co = (8, 120, 120, 256, 64) if which == "ffn" else (8, 60, 60, 512, 128)
+    h, dw_w, dw_b = rn(N * H * W, C).half(), (rn(9, C) * 0.3).half(), rn(C)
+    w2, b2, res, g1, be1 = (rn(Co, C) * 0.05).half(), rn(Co), rn(N * H * W, Co), rn(Co), rn(Co)
+    xn = torch.empty(N * H * W, Co, device="cuda", dtype=torch.half)
+    fn = lambda: ops.mixffn_tail(h, N, H, W, dw_w, dw_b, w2, b2, res, res, g1, be1, 1e-6, xn)
 elif which == "head_fuse":
     N, C = 8, 256
     sizes = [(120, 120), (60, 60), (30, 30), (15, 15)]
@@ -68,9 +74,9 @@ if os.environ.get("TIME"):
     ts = []
     for _ in range(30):
         flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(); fn(); ev1.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b) * 1e3)
+        ts.append(ev0.elapsed_time(ev1) * 1e3)
     ts.sort()
     print(f"{which}: median {ts[len(ts) // 2]:.2f} us, min {ts[0]:.2f} us (cold L2, CUDA events)")

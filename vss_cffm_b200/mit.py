@@ -29,6 +29,7 @@ from .registry import BACKBONES
 from .workspace import Workspace
 
 _H, _F = torch.float16, torch.float32
+_FFN_FUSED = __import__("os").environ.get("CFFM_FFN_FUSED", "1") != "0"   # 0: separate dwconv and fc2 kernels (A/B runs)
 
 
 def _round_up(x, m):
@@ -278,9 +279,19 @@ class MixVisionTransformer(nn.Module):
                 Ch = b["f1w"].shape[0]
                 h1 = ws.get(f"s{s}.h1", (M, Ch), _H)
                 ops.gemm(xn, b["f1w"], bias=b["f1b"], out16=h1)
+                # ---- x += fc2(GELU(dwconv(h1))) ; then the next block's norm1 or the stage norm
+                if fuse_ln and _FFN_FUSED and ops.mixffn_tail_supported(C, Ch):
+                    # one kernel: the convolved / activated hidden map never leaves the SM (csrc/mixffn_sm100.cu)
+                    if bi + 1 < nblk:
+                        nb = st["blocks"][bi + 1]
+                        ops.mixffn_tail(h1, N, Ho, Wo, b["dww"], b["dwb"], b["f2w"], b["f2b"], xres, xres,
+                                        nb["n1g"], nb["n1b"], nb["n1eps"], xn)
+                    else:
+                        ops.mixffn_tail(h1, N, Ho, Wo, b["dww"], b["dwb"], b["f2w"], b["f2b"], xres, None,
+                                        st["fg"], st["fb"], st["feps"], out)
+                    continue
                 h2 = ws.get(f"s{s}.h2", (M, Ch), _H)
                 ops.dwconv3x3_gelu(h1, b["dww"], b["dwb"], h2, N, Ho, Wo, Ch)
-                # ---- x += fc2(...) ; then the next block's norm1 or the stage norm
                 if fuse_ln:
                     if bi + 1 < nblk:
                         nb = st["blocks"][bi + 1]

@@ -134,6 +134,29 @@ def conv_gemm_splitk(x, n, H, W, C, k, stride, pad, w, partials):
               partials.shape[0], _stream())
 
 
+def mixffn_tail_supported(N, hidden):
+    """True when the fused dwconv + GELU + fc2 (+ residual + LayerNorm) kernel takes this (output width, hidden width)."""
+    return bool(_abi.load().cffm_mixffn_tail_supported(int(N), int(hidden)))
+
+
+def mixffn_tail(h, n, H, W, dw_w9c, dw_b, w2, b2, residual, out32, ln_gamma=None, ln_beta=None, ln_eps=0.0, ln_out16=None):
+    """x = residual + (GELU(dwconv3x3(h) + dw_b)) @ w2.T + b2 -> out32 (optional, may alias residual);
+    LayerNorm(x) -> ln_out16 (optional).  h fp16 [n*H*W, hidden] (NHWC), residual fp32 [n*H*W, N]."""
+    _chk(h, _H, "mixffn_tail.h"); _chk(dw_w9c, _H, "mixffn_tail.dw_w"); _chk(dw_b, _F, "mixffn_tail.dw_b")
+    _chk(w2, _H, "mixffn_tail.w2"); _chk(b2, _F, "mixffn_tail.b2"); _chk(residual, _F, "mixffn_tail.residual")
+    HD, N = w2.shape[1], w2.shape[0]
+    M = n * H * W
+    assert h.is_contiguous() and h.numel() == M * HD and tuple(dw_w9c.shape) == (9, HD) and dw_w9c.is_contiguous()
+    assert residual.is_contiguous() and tuple(residual.shape) == (M, N)
+    for t, dt in ((out32, _F), (ln_out16, _H)):
+        if t is not None:
+            _chk(t, dt, "mixffn_tail.out"); assert t.is_contiguous() and tuple(t.shape) == (M, N)
+    if ln_out16 is not None:
+        _chk(ln_gamma, _F, "mixffn_tail.gamma"); _chk(ln_beta, _F, "mixffn_tail.beta")
+    _abi.call("cffm_mixffn_tail", _ptr(h), n, H, W, HD, _ptr(dw_w9c), _ptr(dw_b), _ptr(w2), _ld(w2), _ptr(b2), _ptr(residual),
+              _ptr(out32), _ptr(ln_gamma), _ptr(ln_beta), float(ln_eps), _ptr(ln_out16), N, _stream())
+
+
 def layernorm_sum(partials, bias, gamma, beta, eps, out16=None, out32=None):
     """LayerNorm(sum_s partials[s] + bias)."""
     _chk(partials, _F, "layernorm_sum.partials")
