@@ -19,15 +19,22 @@
 // Per item:
 //   S[128 x 288] = Qbd K^T  M = 128 rows = (head 0: 49 queries | pad to 64 | head 1: 49 queries | pad), K = 64 channels with
 //                           Q block-diagonal (head-0 rows carry zeros in head 1's channels and vice versa), so ONE
-//                           M = 128 MMA computes both heads at the tensor-core cost of two M = 64 ones.
+//                           M = 128 MMA computes both heads at the tensor-core cost of two M = 64 ones.  S is produced and
+//                           released in two halves (columns [0,128) and [128,288)).
 //   softmax                 16 warps, thread = (row, quarter of each 64-key chunk); logits t = S + bias / scale straight out
-//                           of TMEM (one FHFMA per element: fp16 bias operand, fp32 accumulator), exact two-pass row
-//                           maximum, p = 2^((t - m) scale log2 e) -> fp16 P chunks in shared memory (swizzled A operand)
-//   O[128 x 64] += P V      B = V chunk MN-major as loaded; only the diagonal 32-column blocks are read back
-//   epilogue                O / rowsum -> fp16, window_reverse + crop (:812-821) fused into the store
-// Warp roles: 0..15 softmax / epilogue, 16 producer (TMA, block-diagonal Q through cp.async, the item's key mask), 17 TMEM
-// allocator + MMA issuer.  K and Q are single-buffered (those of item i+1 are loaded while the softmax of item i runs), V
-// is double-buffered (loaded a whole item ahead), O is double-buffered in TMEM, P goes through a two-chunk ring.
+//                           of TMEM (one FHFMA per element: fp16 bias operand, fp32 accumulator).  Pass 1: upper bound of the
+//                           row maximum (raw S + the largest bias of the thread's piece; softmax is shift-invariant, so the
+//                           result is the exact softmax).  Pass 2: p = 2^((t - m) scale log2 e), one FFMA + one MUFU.EX2 per
+//                           element, packed to fp16 and written back into TENSOR MEMORY (tcgen05.st): P never goes through
+//                           shared memory, there is no proxy fence in the item loop.
+//   O[128 x 64] += P V      TS-mode tcgen05.mma: A = P chunk from TMEM (three-chunk ring), B = V chunk MN-major as loaded;
+//                           only the diagonal 32-column blocks are read back
+//   epilogue                O / rowsum -> fp16 -> swizzled staging tile -> whole 64-byte row segments; window_reverse + crop
+//                           (:812-821) fused into the store
+// Warp roles: 0..15 softmax / epilogue, 16 producer (TMA boxes under elect.sync, block-diagonal Q through cp.async, the item's
+// key mask), 17 TMEM allocator + P V issuer, 18 Q K^T issuer (two issue warps on two schedulers: as one warp the P V issue fell
+// ~1300 cycles behind the softmax).  K and Q are single-buffered (those of item i+1 are loaded while the softmax of item i
+// runs), V is double-buffered (loaded a whole item ahead), O is double-buffered in TMEM.
 #include <cuda.h>
 
 #include <type_traits>
@@ -57,8 +64,9 @@ constexpr int X_FLOATS = 2 * 4 * 128;                        // [max | sum][colu
 constexpr int KV_BYTES = NPAD * ROWB;
 constexpr int TX_BYTES = REND * ROWB;
 constexpr int BIAS_BYTES = 2 * 49 * BPITCH * 2;
+constexpr int O_STAGE_BYTES = 4 * 32 * 64;                   // output staging tile of the epilogue
 constexpr int CFM_SMEM = 3 * KV_BYTES + 2 * Q_BYTES + BIAS_BYTES + 2 * (NPAD + 4) * 4 /*mask + item coordinates*/ +
-                         2 * X_FLOATS * 4 /*row max / sum exchange, two item parities*/ + 256 /*barriers*/ + 1024 /*align slack*/;
+                         2 * X_FLOATS * 4 /*row max / sum exchange, two item parities*/ + O_STAGE_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
 constexpr int TMEM_O = NPAD;                                 // two O buffers of 64 columns behind S ...
 constexpr int TMEM_P = TMEM_O + 2 * CPAIR;                   // ... and the P ring behind them: 288 + 128 + 96 = 512 columns
 static_assert(TMEM_P + P_RING * P_COLS <= 512, "TMEM budget");
@@ -114,7 +122,7 @@ __device__ __forceinline__ void cfm_masked(const uint32_t* u, const float* mask_
 //     when the phase is already complete: P therefore never goes through shared memory (tcgen05.st into TMEM, A operand of
 //     a TS-mode MMA), and there is one mbarrier wait per chunk, placed ahead of the math;
 //   * MUFU.EX2 (16 lanes / clock / SM: 512 cycles per 64-key chunk) is the floor of pass 2.
-__device__ __forceinline__ void softmax_role(const CfmParams& p, const __half* sBias, const float* sMask, float* sX,
+__device__ __forceinline__ void softmax_role(const CfmParams& p, const __half* sBias, const float* sMask, float* sX, uint8_t* sO,
                                           const CfmBars& bar, uint32_t tmem_base, int hp, int slot, int nslots) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wq = warp & 3, cq = warp >> 2;                   // TMEM lane quarter, column quarter of every chunk
@@ -154,15 +162,24 @@ __device__ __forceinline__ void softmax_role(const CfmParams& p, const __half* s
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&bar.o_empty[ob]);
     { const uint32_t it = e_it; if (stid == 0) CFM_PROF(18); }
-    const int y = WS * wi + q / WS, x = WS * wj + q % WS;
-    if (q < 49 && y < p.H && x < p.W) {
-      __half* dst = p.out + ((static_cast<int64_t>(b) * p.H + y) * p.W + x) * 256 + hp * CPAIR + hl * 32 + cq * 8;
-      uint4 wv;
-      wv.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-      wv.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-      wv.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-      wv.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-      *reinterpret_cast<uint4*>(dst) = wv;
+    uint4 wv;
+    wv.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+    wv.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+    wv.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+    wv.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+    // A thread-per-row store sends 32 separate 16-byte pieces per instruction through the L1 (32 wavefronts).  The 32 rows x 64
+    // bytes of this lane quarter go through a swizzled staging tile instead (piece j of row r at j ^ ((r >> 1) & 3): conflict-
+    // free both ways) and leave as whole 64-byte row segments, eight rows per instruction.
+    uint8_t* sq = sO + wq * (32 * 64);
+    *reinterpret_cast<uint4*>(sq + lane * 64 + ((cq ^ ((lane >> 1) & 3)) << 4)) = wv;
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_rows) : "memory");
+    {
+      const int t = cq * 32 + lane, rl = t >> 2, j = t & 3;
+      const int q2 = (wq * 32 + rl) & 63;                    // query of the staged row (same head: a quarter never straddles 64)
+      const uint4 val = *reinterpret_cast<const uint4*>(sq + rl * 64 + ((j ^ ((rl >> 1) & 3)) << 4));
+      const int y = WS * wi + q2 / WS, x = WS * wj + q2 % WS;
+      if (q2 < 49 && y < p.H && x < p.W)
+        *reinterpret_cast<uint4*>(p.out + ((static_cast<int64_t>(b) * p.H + y) * p.W + x) * 256 + hp * CPAIR + hl * 32 + j * 8) = val;
     }
     { const uint32_t it = e_it; if (stid == 0) CFM_PROF(19); }
   };
@@ -174,11 +191,13 @@ __device__ __forceinline__ void softmax_role(const CfmParams& p, const __half* s
     float* xm = sX + (it & 1u) * X_FLOATS;
     uint32_t sb[2][16];                                      // two register sets: chunk C lives in sb[C & 1]
     if (stid == 0) CFM_PROF(8);
+    ptx::mbar_wait(&bar.s_full[0], it & 1u);
+    if (stid == 0) CFM_PROF(14);
     ptx::mbar_wait(&bar.m_full[it & 1u], (it >> 1) & 1u);
+    if (stid == 0) CFM_PROF(15);
     // {clip, window row, window column} of this item: read NOW -- after the last read of S the producer may rewrite the buffer
     const int4 info = *reinterpret_cast<const int4*>(mask + NPAD);
     const int cb = info.x, cwi = info.y, cwj = info.z;
-    ptx::mbar_wait(&bar.s_full[0], it & 1u);
     ptx::tc_fence_after();
     if (stid == 0) CFM_PROF(9);
     cfm_issue_load<0>(lane_addr, cq, sb[0]);
@@ -282,7 +301,8 @@ cfm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_co
   __half* sBias = reinterpret_cast<__half*>(sQ + 2 * Q_BYTES);
   float* sMask = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sBias) + BIAS_BYTES);
   float* sX = sMask + 2 * (NPAD + 4);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 2 * X_FLOATS);
+  uint8_t* sO = reinterpret_cast<uint8_t*>(sX + 2 * X_FLOATS);   // output staging: 4 lane quarters x [32 rows][64 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + O_STAGE_BYTES);
   uint64_t* k_full = bars + 0;     // TMA -> Q K^T issuer: K tile landed (transaction bytes)
   uint64_t* kq_empty = bars + 1;   // Q K^T issuer -> producer: Q K^T of an item retired: K and that item's Q buffer may be overwritten
   uint64_t* q_full = bars + 2;     // [2] producer warp -> Q K^T issuer: block-diagonal Q written
@@ -378,8 +398,9 @@ cfm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_co
   if (warp == SM_WARPS) {
     // ===================== producer: TMA K / V boxes, block-diagonal Q, key mask =====================
     const int Wa = p.nWw * WS + 2 * RING, Ha = p.nWh * WS + 2 * RING;
-    auto boxes = [&](uint8_t* dst, uint64_t* fb, int item, int ct, int cp) {   // ct / cp: channel of K (or V) in qkv / pooled rows
-      const int b = item / nW, w = item - b * nW, wi = w / p.nWw, wj = w - wi * p.nWw;
+    struct Win { int b, wi, wj; };                             // clip, window row, window column of an item
+    auto boxes = [&](uint8_t* dst, uint64_t* fb, const Win& c, int ct, int cp) {   // ct / cp: channel of K (or V) in qkv / pooled rows
+      const int b = c.b, wi = c.wi, wj = c.wj;
       // where the three reference frames of this clip live (frame-sharded runs read the all-gathered buffer in place)
       int sl[3] = {b, b, b}, rk[3] = {0, 0, 0};
       if (p.ref_slot != nullptr) {
@@ -414,8 +435,8 @@ cfm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_co
 #pragma unroll
     for (int j = 0; j < MP; ++j) m_par[j] = m_tab[lane + 32 * j];
     // Q of an item: 13 cp.async per lane into the block-diagonal tile `buf`; published on q_full[buf] by finish_q
-    auto issue_q = [&](int item, uint32_t buf) {
-      const int b = item / nW, w = item - b * nW, wi = w / p.nWw, wj = w - wi * p.nWw;
+    auto issue_q = [&](const Win& c, uint32_t buf) {
+      const int b = c.b, wi = c.wi, wj = c.wj;
       const __half* qbase = p.qkv_a + ((static_cast<int64_t>(b) * Ha + WS * wi + RING) * Wa + WS * wj + RING) * CQKV + hp * CPAIR;
 #pragma unroll
       for (int j = 0; j < QP; ++j)
@@ -428,34 +449,53 @@ cfm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_co
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&q_full[buf]);
     };
+    // Items advance by nslots windows: the coordinates are stepped without divisions (this warp shares its scheduler with four
+    // busy softmax warps and gets a fifth of the issue slots: sixteen integer divisions per item were most of its work).
+    const int dq = nslots / p.nWw, dr = nslots - dq * p.nWw;
+    auto step = [&](Win c) {
+      c.wj += dr; c.wi += dq;
+      if (c.wj >= p.nWw) { c.wj -= p.nWw; ++c.wi; }
+      while (c.wi >= p.nWh) { c.wi -= p.nWh; ++c.b; }
+      return c;
+    };
+    Win cur;
+    cur.b = slot / nW;
+    cur.wi = (slot - cur.b * nW) / p.nWw;
+    cur.wj = slot - cur.b * nW - cur.wi * p.nWw;
     if (slot < n_items) {                                    // first item: K and Q first (Q K^T needs them), V behind
-      if (lane == 0) boxes(sK, k_full, slot, 256 + hp * CPAIR, hp * CPAIR);
-      issue_q(slot, 0);
-      if (lane == 0) boxes(sV, &v_full[0], slot, 512 + hp * CPAIR, 256 + hp * CPAIR);
-      finish_q(0);
+      if (ptx::elect_one()) boxes(sK, k_full, cur, 256 + hp * CPAIR, hp * CPAIR);
+      __syncwarp();
+      issue_q(cur, 0);
+      if (ptx::elect_one()) boxes(sV, &v_full[0], cur, 512 + hp * CPAIR, 256 + hp * CPAIR);
+      __syncwarp();
     }
     uint32_t it = 0;
     for (int item = slot; item < n_items; item += nslots, ++it) {
-      const int b = item / nW, w = item - b * nW, wi = w / p.nWw, wj = w - wi * p.nWw;
       const int next = item + nslots;
-      // Q K^T of item it-1 has retired: K and the Q buffer of item it-1 (= that of item it+1) are free
+      const Win nxt = step(cur);
+      // Q K^T of item it-1 has retired: K and the Q buffer of item it-1 (= that of item it+1) are free.  K goes out first: it
+      // is single-buffered and its latency is the one on the path to the next S.
       if (it > 0) {
         ptx::mbar_wait(kq_empty, (it - 1) & 1u);
-        if (lane == 0) { CFM_PROF(0); boxes(sK, k_full, item, 256 + hp * CPAIR, hp * CPAIR); }
+        if (lane == 0) CFM_PROF(0);
+        if (ptx::elect_one()) boxes(sK, k_full, cur, 256 + hp * CPAIR, hp * CPAIR);
+        __syncwarp();
       }
-      if (next < n_items) issue_q(next, (it + 1) & 1u);      // Q a whole item ahead; its latency hides behind the mask below
-      // the item's key mask; its buffer was last read for item it-2, whose reads precede kq_empty(it-1)
+      finish_q(it & 1u);                                     // Q of THIS item: its copies were issued a whole item ago
+      if (lane == 0) CFM_PROF(1);
+      // The item's key mask; its buffer was last read for item it-2, whose reads precede kq_empty(it-1).  (The release arrive
+      // below waits for this warp's cp.async copies in flight: with the next item's Q issued ahead of it, m_full came a whole
+      // global-memory latency late and the 16 softmax warps waited ~600 cycles at the top of every item.)
       float* mask = sMask + (it & 1u) * (NPAD + 4);
-      if (lane < 3) reinterpret_cast<int*>(mask + NPAD)[lane] = lane == 0 ? b : (lane == 1 ? wi : wj);   // the softmax warps do not redo the divisions
+      if (lane < 3) reinterpret_cast<int*>(mask + NPAD)[lane] = lane == 0 ? cur.b : (lane == 1 ? cur.wi : cur.wj);   // for the epilogue
 #pragma unroll
       for (int j = 0; j < MP; ++j) {
         const int mp = m_par[j], st = (mp >> 16) & 15, f = mp >> 20;
-        const int y = st * wi + (mp & 255) - 8, x = st * wj + ((mp >> 8) & 255) - 8;
+        const int y = st * cur.wi + (mp & 255) - 8, x = st * cur.wj + ((mp >> 8) & 255) - 8;
         mask[lane + 32 * j] = (f == 0 || (y >= 0 && y < f * p.nWh && x >= 0 && x < f * p.nWw)) ? 0.f : -INFINITY;
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bar.m_full[it & 1u]);
-      if (next < n_items) { finish_q((it + 1) & 1u); if (lane == 0) CFM_PROF(1); }
       if (p.dump != nullptr) {
         ptx::mbar_wait(k_full, it & 1u);
         dump_tile(sK, item, 0);
@@ -463,12 +503,16 @@ cfm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_co
         dump_tile(sV + (it & 1u) * KV_BYTES, item, 1);
         __syncwarp();
       }
-      // V of the NEXT item, a whole item ahead of its first use
       if (next < n_items) {
+        // V of the NEXT item, a whole item ahead of its first use, then its Q copies (published at the top of the next round)
         const uint32_t nb = (it + 1) & 1u;
         if (it >= 1) ptx::mbar_wait(&v_empty[nb], ((it - 1) >> 1) & 1u);
-        if (lane == 0) { CFM_PROF(2); boxes(sV + nb * KV_BYTES, &v_full[nb], next, 512 + hp * CPAIR, 256 + hp * CPAIR); }
+        if (lane == 0) CFM_PROF(2);
+        if (ptx::elect_one()) boxes(sV + nb * KV_BYTES, &v_full[nb], nxt, 512 + hp * CPAIR, 256 + hp * CPAIR);
+        __syncwarp();
+        issue_q(nxt, nb);
       }
+      cur = nxt;
     }
   } else if (warp == SM_WARPS + 1) {
     // ===================== P V issuer =====================
@@ -551,7 +595,7 @@ cfm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_co
   } else {
     ptx::cp_async_wait_all();                                // bias slice (this thread's pieces)
     asm volatile("bar.sync 5, 512;" ::: "memory");           // ... and everybody else's
-    softmax_role(p, sBias, sMask, sX, bar, tmem_base, hp, slot, nslots);
+    softmax_role(p, sBias, sMask, sX, sO, bar, tmem_base, hp, slot, nslots);
   }
   ptx::tc_fence_before();
   __syncthreads();
