@@ -88,10 +88,10 @@ class FrameShardPlan:
         return rank * self.max_slots + slot
 
 
-def all_gather_slots(send, group=None):
+def all_gather_slots(send, group=None, out=None):
     """One all-gather of every rank's [max_slots, ...] buffer -> [G * max_slots, ...] (NCCL on GPUs, gloo in tests)."""
     world = dist.get_world_size(group)
-    recv = send.new_empty((world * send.shape[0],) + tuple(send.shape[1:]))
+    recv = out if out is not None else send.new_empty((world * send.shape[0],) + tuple(send.shape[1:]))
     if dist.get_backend(group) == "gloo":
         dist.all_gather(list(recv.chunk(world, dim=0)), send, group=group)
     else:
@@ -146,15 +146,19 @@ class FrameShardedRunner:
         depth = len(P["blocks"])
         # ---- per-frame work: backbone + folded MLP decoder (cffm_head.py:102-133)
         if n_loc:
-            feats = [head._as_nhwc16(t) for t in model.backbone(frames)]   # no stage hook: projections are issued below
+            proj = [None] * 4
+
+            def project_stage(i, feat):
+                """Folded linear_c{i+1} of ONE stage, on a side stream the moment that stage exists (beside the later stages)."""
+                t = head._as_nhwc16(feat)
+                proj[i] = ws.get(f"p{i}", (t.shape[0] * t.shape[1] * t.shape[2], E), _H, device=dev)
+                with ops.fork("proj"):
+                    ops.gemm(t.reshape(-1, t.shape[3]), P["pw"][i], out16=proj[i])
+
+            feats = [head._as_nhwc16(t) for t in model.backbone(frames, stage_hook=project_stage)]
             sizes = [(t.shape[1], t.shape[2]) for t in feats]
             h, w = sizes[0]
-            proj = [ws.get(f"p{i}", (n_loc * sizes[i][0] * sizes[i][1], E), _H, device=dev) for i in range(4)]
-            with ops.fork():                                     # the three small projections beside the big one
-                for i in (1, 2, 3):
-                    ops.gemm(feats[i].reshape(-1, feats[i].shape[3]), P["pw"][i], out16=proj[i])
-            ops.gemm(feats[0].reshape(-1, feats[0].shape[3]), P["pw"][0], out16=proj[0])
-            ops.join()
+            ops.join("proj")
         else:
             h, w = (H - 1) // 4 + 1, (W - 1) // 4 + 1              # OverlapPatchEmbed k7 s4 p3 (mix_transformer.py:173-195): same on every rank
         h2, w2 = h // 2, w // 2
@@ -170,26 +174,35 @@ class FrameShardedRunner:
         # ONE K/V projection per block over the rank's packed [role 0 maps | role 1 maps | role 2 maps] token buffer.
         role_off, flat_tok = plan.role_offsets(nW)
         send = ws.get("send", (depth, flat_tok, 2 * E), _H, device=dev, zero=True)
-        if n_ref:
-            xn = ws.get("xn_ref", (n_ref * HW, E), _H, device=dev)
-            pooled = ws.get("pooled_refs", (flat_tok, E), _H, device=dev, zero=True)     # rows of unused slots stay zero
-            for i, b in enumerate(P["blocks"]):
-                ops.cffa_norm_frames(x32[:n_ref * HW], b["n1g"], b["n1b"], b["n1eps"], xn, None, n_ref, n_ref, h2, w2, Hp, Wp, E)
-                first = 0
-                for k, per in enumerate(ROLE_TOKENS):
-                    n_k = plan.role_count[self.rank][k]
-                    if n_k:
-                        ops.cffa_pool_level(xn[first * HW:(first + n_k) * HW], n_k, k + 1, h2, w2, E, b["pool_w"], b["pool_b"],
-                                            pooled[role_off[k]:role_off[k] + n_k * per * nW])
-                    first += n_k
-                ops.gemm(pooled, b["qkv_w"][E:], bias=b["qkv_b"][E:], out16=send[i])
-        # ---- the one collective of the path, on a side stream: it overlaps norm1 / pooling / the QKV GEMM of the first block
-        # (SURVEY.md 8e); the CFM kernel then reads the gathered buffer IN PLACE through a per-clip slot table
+        # ---- the exchange, block by block, on a side stream beside the target frames' path: the K/V of block i
+        # are gathered as soon as they exist, the CFM launch of block i waits for ITS gather only -- the reference-frame work
+        # and the all-gather of block i+1 run under block i's attention and FFN.  The CFM kernel reads the gathered buffer IN
+        # PLACE through a per-clip slot table.
         if plan.G > 1:
-            with ops.fork("gather"):
-                gathered = all_gather_slots(send, self.group).view(plan.G, depth, flat_tok, 2 * E)
+            gathered = ws.get("gathered", (depth, plan.G, flat_tok, 2 * E), _H, device=dev)
         else:
-            gathered = send.view(1, depth, flat_tok, 2 * E)
+            gathered = send.view(depth, 1, flat_tok, 2 * E)
+        ready = []
+        with ops.fork("gather"):
+            if n_ref:
+                xn = ws.get("xn_ref", (n_ref * HW, E), _H, device=dev)
+                pooled = ws.get("pooled_refs", (flat_tok, E), _H, device=dev, zero=True)     # rows of unused slots stay zero
+            for i, b in enumerate(P["blocks"]):
+                if n_ref:
+                    ops.cffa_norm_frames(x32[:n_ref * HW], b["n1g"], b["n1b"], b["n1eps"], xn, None, n_ref, n_ref, h2, w2, Hp, Wp, E)
+                    first = 0
+                    for k, per in enumerate(ROLE_TOKENS):
+                        n_k = plan.role_count[self.rank][k]
+                        if n_k:
+                            ops.cffa_pool_level(xn[first * HW:(first + n_k) * HW], n_k, k + 1, h2, w2, E, b["pool_w"], b["pool_b"],
+                                                pooled[role_off[k]:role_off[k] + n_k * per * nW])
+                        first += n_k
+                    ops.gemm(pooled, b["qkv_w"][E:], bias=b["qkv_b"][E:], out16=send[i])
+                if plan.G > 1:
+                    all_gather_slots(send[i], self.group, out=gathered[i].view(plan.G * flat_tok, 2 * E))
+                ev = torch.cuda.Event()
+                ev.record()                                      # on the side stream: block i's reference K/V are in place
+                ready.append(ev)
         if not n_t:
             ops.join("gather")
             return torch.empty(0, H, W, dtype=torch.int64, device=dev)
@@ -211,14 +224,14 @@ class FrameShardedRunner:
             ops.cffa_pool_level(xn_t, n_t, 0, h2, w2, E, b["pool_w"], b["pool_b"], pooled_t)
             ops.gemm(xt_pad, b["qkv_w"], bias=b["qkv_b"], out16=qkv_t)
             ops.gemm(pooled_t, b["qkv_w"][E:], bias=b["qkv_b"][E:], out16=kv_t)
-            if i == 0:
-                ops.join("gather")
-            ops.cfm_attention_slots(qkv_t, kv_t, gathered[:, i], role_off, plan.role_slots, slots, b["bias"], ao, n_t, h2, w2, E, HEADS,
+            torch.cuda.current_stream().wait_event(ready[i])
+            ops.cfm_attention_slots(qkv_t, kv_t, gathered[i], role_off, plan.role_slots, slots, b["bias"], ao, n_t, h2, w2, E, HEADS,
                                     (E // HEADS) ** -0.5)
             ops.gemm(ao, b["proj_w"], bias=b["proj_b"], residual=xt, out32=xt)
             ops.layernorm(xt, b["n2g"], b["n2b"], b["n2eps"], out16=xn2)
             ops.gemm(xn2, b["f1w"], bias=b["f1b"], out16=hid, act=ops.ACT_GELU)
             ops.gemm(hid, b["f2w"], bias=b["f2b"], residual=xt, out32=xt, out16=xt16 if i == depth - 1 else None)
+        ops.join("gather")
         # ---- classifier + fused x2 / x4 resize + argmax (cffm_head.py:145-149, encoder_decoder.py:373-377,564)
         lg = ws.get("lg", (n_t * HW, P["ncp"]), _F, device=dev)
         ops.gemm(ct16, P["pred2_w"][:, :E], bias=P["pred2_b"], out32=lg)
