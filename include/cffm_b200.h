@@ -113,6 +113,18 @@ int cffm_conv_gemm_f16_ln(const void* x, int n, int H, int W, int C, int ksize, 
 int cffm_conv_gemm_f16_splitk(const void* x, int n, int H, int W, int C, int ksize, int stride, int pad,
                               const void* Wt, int64_t ldw, float* partials, int Nout, int splits, void* stream);
 
+/* Stage-1 OverlapPatchEmbed in ONE kernel (no patch matrix): y = LayerNorm(conv7x7_s4_p3(x) + bias; gamma1, beta1) -> out_f32
+ * [n*Ho*Wo, Nout] (the fp32 residual stream), LayerNorm(y; gamma2, beta2) -> ln_out_f16 (the first block's norm1).
+ * OverlapPatchEmbed.forward mix_transformer.py:173-200 followed by Block.norm1 :154.
+ *   x  fp32 [n, 3, H, W] (NCHW, the normalised frames), W %% 4 == 0;
+ *   Wk fp16 [Nout, 192]: Wk[o, (c*7 + ky)*8 + kx] = conv.weight[o, c, ky, kx], zero elsewhere (kx = 7, columns >= 168).
+ * cffm_patch_embed_s1_supported(...) != 0 names what it is built for (3 channels, k7 s4 p3, Nout in {32, 64}); other
+ * geometries: cffm_im2col + cffm_gemm_f16_ln_chain. */
+int cffm_patch_embed_s1_supported(int W, int Cin, int ksize, int stride, int pad, int Nout);
+int cffm_patch_embed_s1(const float* x, int n, int H, int W, const void* Wk, const float* bias, const float* gamma1,
+                        const float* beta1, float eps1, const float* gamma2, const float* beta2, float eps2,
+                        float* out_f32, void* ln_out_f16, int Nout, void* stream);
+
 /* Mix-FFN tail in ONE kernel: x_out = residual + fc2(GELU(dwconv3x3(hidden) + dw_b)) + b2, and optionally
  * LayerNorm(x_out; gamma, beta, eps) -> ln_out_f16.  Replaces Mlp.dwconv + act + fc2 (mix_transformer.py:52-58, DWConv
  * :361-368), the residual add and the next norm (Block.forward :84-88): the convolved / activated hidden map stays on chip.

@@ -169,6 +169,28 @@ def test_dwconv3x3_gelu(ops, N, H, W, C):
     check(out, ref, REL16, "dwconv+gelu")
 
 
+@pytest.mark.parametrize("n,H,W,N", [(2, 64, 96, 64), (1, 480, 480, 64), (3, 37, 52, 32), (2, 480, 864, 64), (1, 20, 16, 64)])
+def test_patch_embed_s1(ops, n, H, W, N):
+    """conv 7x7 s4 p3 + bias -> LayerNorm -> LayerNorm in one kernel == the fp64 composition (mix_transformer.py:173-200, :154)."""
+    assert ops.patch_embed_s1_supported(W, 3, 7, 4, 3, N) and not ops.patch_embed_s1_supported(W + 1, 3, 7, 4, 3, N)
+    x = synth.synth_array((n, 3, H, W), 71)
+    w = h16(synth.synth_array((N, 3, 7, 7), 72, scale=147 ** -0.5))
+    b = synth.synth_array((N,), 73, scale=0.1)
+    g1, e1 = 1 + synth.synth_array((N,), 74, scale=0.1), synth.synth_array((N,), 75, scale=0.1)
+    g2, e2 = 1 + synth.synth_array((N,), 76, scale=0.1), synth.synth_array((N,), 77, scale=0.1)
+    y = F.conv2d(h16(x).double(), w.double(), b.double(), stride=4, padding=3)      # the kernel rounds the frames to fp16 (MMA operand)
+    Ho, Wo = y.shape[2:]
+    y = y.permute(0, 2, 3, 1).reshape(n * Ho * Wo, N)
+    y1 = F.layer_norm(y, (N,), g1.double(), e1.double(), 1e-5)
+    y2 = F.layer_norm(y1, (N,), g2.double(), e2.double(), 1e-6)
+    out32 = torch.empty(n * Ho * Wo, N, device="cuda")
+    out16 = torch.empty(n * Ho * Wo, N, dtype=torch.float16, device="cuda")
+    ops.patch_embed_s1(x.cuda().contiguous(), ops.patch_embed_s1_weight(w.cuda()), b.cuda(), g1.cuda(), e1.cuda(), 1e-5, g2.cuda(), e2.cuda(),
+                       1e-6, out32, out16)
+    check(out32, y1, 1e-3, "patch_embed LayerNorm 1")
+    check(out16, y2, REL16, "patch_embed LayerNorm 2")
+
+
 @pytest.mark.parametrize("n,H,W,HD,N,ln,alias", [(2, 16, 24, 256, 64, True, True), (1, 7, 5, 128, 64, False, True),
                                                  (3, 30, 33, 512, 128, True, True), (2, 120, 120, 256, 64, True, False),
                                                  (1, 9, 70, 256, 128, True, False), (2, 60, 60, 512, 128, False, True)])

@@ -34,6 +34,8 @@ SIGNATURES = {
     "cffm_splitk_plan": ([i32, i32, i32], i32),
     "cffm_conv_gemm_f16_ln": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, vp, i64, vp, vp, f32, vp, vp, f32, vp, i64, i32, vp], i32),
     "cffm_conv_gemm_f16_splitk": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, i32, i32, vp], i32),
+    "cffm_patch_embed_s1_supported": ([i32, i32, i32, i32, i32, i32], i32),
+    "cffm_patch_embed_s1": ([vp, i32, i32, i32, vp, vp, vp, vp, f32, vp, vp, f32, vp, vp, i32, vp], i32),
     "cffm_mixffn_tail_supported": ([i32, i32], i32),
     "cffm_mixffn_tail": ([vp, i32, i32, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, f32, vp, i32, vp], i32),
     "cffm_layernorm_sum": ([vp, i32, vp, vp, vp, f32, vp, i64, vp, i64, i32, i32, vp], i32),

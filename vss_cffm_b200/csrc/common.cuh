@@ -62,6 +62,7 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 int make_tmap(struct CUtensorMap_st* tm, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows);
 int make_tmap_nd(struct CUtensorMap_st* tm, const void* base, int rank, const int64_t* dims, const int64_t* strides, const int* box);
 int make_tmap_4d(struct CUtensorMap_st* tm, const void* base, const int64_t dims[4], const int64_t strides[3], const int box[4]);
+int make_tmap_f32_4d(struct CUtensorMap_st* tm, const void* base, const int64_t dims[4], const int64_t strides[3], const int box[4]);
 int num_sms();
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -596,6 +596,23 @@ static int make_tmap_conv(CUtensorMap* tm, const ConvDesc& cv) {
 }
 
 // fp16 [rows, cols] output (row stride ld elements) as the target of per-warp 32 x 32 bulk stores (64-byte swizzle).
+// 4-D fp32 tensor map without swizzle (dims / box innermost first, strides in ELEMENTS of dims 1..3): the NCHW input frames
+// of the stage-1 patch embedding.  Shared: common.cuh.
+int make_tmap_f32_4d(CUtensorMap* tm, const void* base, const int64_t dims[4], const int64_t strides[3], const int box[4]) {
+  EncodeTiledFn fn = get_encode_fn();
+  CFFM_REQUIRE(fn != nullptr, CFFM_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[4], gstride[3];
+  cuuint32_t bx[4], estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) { gdim[i] = static_cast<cuuint64_t>(dims[i]); bx[i] = static_cast<cuuint32_t>(box[i]); }
+  for (int i = 0; i < 3; ++i) gstride[i] = static_cast<cuuint64_t>(strides[i]) * 4;
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstride, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CFFM_REQUIRE(r == CUDA_SUCCESS, CFFM_E_DRIVER, "cuTensorMapEncodeTiled (fp32 4-D) failed with CUresult %d (dims %lld %lld %lld %lld, box %d %d %d)",
+               static_cast<int>(r), (long long)dims[0], (long long)dims[1], (long long)dims[2], (long long)dims[3], box[0], box[1], box[2]);
+  return CFFM_OK;
+}
+
 static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld) {
   EncodeTiledFn fn = get_encode_fn();
   CFFM_REQUIRE(fn != nullptr, CFFM_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");

@@ -203,13 +203,16 @@ __device__ __forceinline__ void mha_softmax_role(const MhaParams& p, float* sX, 
                 sum0 += p0; sum1 += p1;
                 hh[j] = pack_half2(p0, p1);
               }
-            } else {                                         // the piece that straddles N_kv (or lies beyond it)
-#pragma unroll
+            } else {                                         // the piece that straddles N_kv (or lies beyond it): key pairs past
+#pragma unroll                                               // the end cost no exponentials (warp-uniform branches)
               for (int j = 0; j < 8; ++j) {
-                const float p0 = col0 + 2 * j < kb ? ptx::ex2_approx(fmaf(__uint_as_float(s[2 * j]), scl, -msc)) : 0.f;
-                const float p1 = col0 + 2 * j + 1 < kb ? ptx::ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), scl, -msc)) : 0.f;
-                sum0 += p0; sum1 += p1;
-                hh[j] = pack_half2(p0, p1);
+                hh[j] = 0u;
+                if (col0 + 2 * j < kb) {
+                  const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * j]), scl, -msc));
+                  const float p1 = col0 + 2 * j + 1 < kb ? ptx::ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), scl, -msc)) : 0.f;
+                  sum0 += p0; sum1 += p1;
+                  hh[j] = pack_half2(p0, p1);
+                }
               }
             }
             if (!slot_free) ptx::mbar_wait(&bar.p_empty[ps], pph);

@@ -30,6 +30,7 @@ from .workspace import Workspace
 
 _H, _F = torch.float16, torch.float32
 _FFN_FUSED = __import__("os").environ.get("CFFM_FFN_FUSED", "1") != "0"   # 0: separate dwconv and fc2 kernels (A/B runs)
+_PE_FUSED = __import__("os").environ.get("CFFM_PE_FUSED", "1") != "0"     # 0: im2col + GEMM for the stage-1 patch embedding
 
 
 def _round_up(x, m):
@@ -207,11 +208,19 @@ class MixVisionTransformer(nn.Module):
             # fill = zero padding) whenever the image is fp16 NHWC with C % 64 == 0 (stages 2-4); the fp32 NCHW input frames
             # of stage 1 (3 channels) go through a patch matrix.
             implicit = layout == 1 and ops.conv_gemm_supported(st["cin"], Wo, stride) and (S > 1 or C <= 128)
-            if not implicit:
+            fused_pe = layout == 0 and _PE_FUSED and ops.patch_embed_s1_supported(W, st["cin"], k, stride, pad, C)
+            if fused_pe:
+                # stage 1: convolution of the fp32 NCHW frames, both norms, one kernel, no patch matrix (csrc/patch_embed_sm100.cu)
+                if "wk" not in st:
+                    st["wk"] = ops.patch_embed_s1_weight(self.patch_embed1.proj.weight)
+                ops.patch_embed_s1(cur, st["wk"], st["b"], st["ng"], st["nb"], st["eps"], b0["n1g"], b0["n1b"], b0["n1eps"], xres, xn)
+            elif not implicit:
                 col = ws.get(f"s{s}.col", (M, st["kpad"]), _H)
                 ops.im2col(cur, layout, N, H, W, st["cin"], k, stride, pad, col)
             # patch-embed norm and the first block's norm1 in one pass (the row stays in registers in between)
-            if S > 1:
+            if fused_pe:
+                pass                                             # done above
+            elif S > 1:
                 if implicit:
                     ops.conv_gemm_splitk(cur, N, H, W, st["cin"], k, stride, pad, st["w"], pe32)
                 else:

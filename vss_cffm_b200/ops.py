@@ -134,6 +134,37 @@ def conv_gemm_splitk(x, n, H, W, C, k, stride, pad, w, partials):
               partials.shape[0], _stream())
 
 
+def patch_embed_s1_supported(W, cin, k, stride, pad, nout):
+    """True when the fused stage-1 patch-embedding kernel takes this convolution."""
+    return bool(_abi.load().cffm_patch_embed_s1_supported(int(W), int(cin), int(k), int(stride), int(pad), int(nout)))
+
+
+def patch_embed_s1_weight(conv_weight):
+    """conv.weight [Nout, 3, 7, 7] -> the kernel's fp16 [Nout, 192] layout: column (c*7 + ky)*8 + kx, zero padding."""
+    o, c, kh, kw = conv_weight.shape
+    assert (c, kh, kw) == (3, 7, 7)
+    w = torch.zeros(o, c * kh, 8, dtype=torch.float32, device=conv_weight.device)
+    w[:, :, :kw] = conv_weight.detach().float().reshape(o, c * kh, kw)
+    out = torch.zeros(o, 192, dtype=_H, device=conv_weight.device)
+    out[:, :c * kh * 8] = w.reshape(o, c * kh * 8).to(_H)
+    return out
+
+
+def patch_embed_s1(x, wk, bias, g1, b1, eps1, g2, b2, eps2, out32, ln_out16):
+    """LayerNorm(conv7x7 s4 p3 (x) + bias) -> out32; LayerNorm of that -> ln_out16.  x fp32 [n, 3, H, W] contiguous."""
+    _chk(x, _F, "patch_embed_s1.x", rows2d=False); _chk(wk, _H, "patch_embed_s1.w"); _chk(out32, _F, "patch_embed_s1.out32")
+    _chk(ln_out16, _H, "patch_embed_s1.ln_out16")
+    n, c, H, W = x.shape
+    N = wk.shape[0]
+    Ho, Wo = (H - 1) // 4 + 1, (W - 1) // 4 + 1
+    assert x.is_contiguous() and c == 3 and tuple(wk.shape) == (N, 192) and wk.is_contiguous()
+    assert out32.is_contiguous() and ln_out16.is_contiguous() and tuple(out32.shape) == (n * Ho * Wo, N) == tuple(ln_out16.shape)
+    for t in (bias, g1, b1, g2, b2):
+        _chk(t, _F, "patch_embed_s1.vector"); assert t.numel() == N
+    _abi.call("cffm_patch_embed_s1", _ptr(x), n, H, W, _ptr(wk), _ptr(bias), _ptr(g1), _ptr(b1), float(eps1), _ptr(g2), _ptr(b2),
+              float(eps2), _ptr(out32), _ptr(ln_out16), N, _stream())
+
+
 def mixffn_tail_supported(N, hidden):
     """True when the fused dwconv + GELU + fc2 (+ residual + LayerNorm) kernel takes this (output width, hidden width)."""
     return bool(_abi.load().cffm_mixffn_tail_supported(int(N), int(hidden)))
