@@ -1,5 +1,5 @@
 """Launch ONE hot kernel of the path a few times on production shapes (B=2 clips, T=4, 480x480, MiT-B1), for
-`ncu --set full -s 2 -c 1`.  usage: python tools/one_kernel.py <gemm_fc1|gemm_fc2|gemm_q|dwconv|ffn|ffn_s2|head_fuse|argmax|mha|cfm|ln>"""
+`ncu --set full -s 2 -c 1`.  usage: python tools/one_kernel.py <gemm_fc1|gemm_fc2|gemm_q|dwconv|ffn|ffn_s2|patch_embed|head_fuse|argmax|mha|cfm|ln>"""
 import os
 import sys
 
@@ -28,6 +28,12 @@ elif which == "dwconv":
     N, H, W, C = 8, 120, 120, 256
     x, w, b, out = rn(N, H, W, C).half(), (rn(9, C) * 0.3).half(), rn(C), torch.empty(N, H, W, C, device="cuda", dtype=torch.half)
     fn = lambda: ops.dwconv3x3_gelu(x, w, b, out, N, H, W, C)
+elif which == "patch_embed":
+    N, H, W, Co = 8, 480, 480, 64
+    x, wk = rn(N, 3, H, W), ops.patch_embed_s1_weight((rn(Co, 3, 7, 7) * 0.08).half())
+    pb, g1, e1, g2, e2 = rn(Co), rn(Co), rn(Co), rn(Co), rn(Co)
+    o32, o16 = torch.empty(N * 120 * 120, Co, device="cuda"), torch.empty(N * 120 * 120, Co, device="cuda", dtype=torch.half)
+    fn = lambda: ops.patch_embed_s1(x, wk, pb, g1, e1, 1e-5, g2, e2, 1e-6, o32, o16)
 elif which in ("ffn", "ffn_s2"):
     N, H, W, C, Co = (8, 120, 120, 256, 64) if which == "ffn" else (8, 60, 60, 512, 128)
     h, dw_w, dw_b = rn(N * H * W, C).half(), (rn(9, C) * 0.3).half(), rn(C)

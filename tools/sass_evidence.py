@@ -23,7 +23,7 @@ for f in re.split(r"\n\s*Function : ", txt)[1:]:
     name = re.sub(r"cffm::\(anonymous namespace\)::", "", name)
     name = re.sub(r"\((int|bool)\)", "", re.sub(r"cffm::<unnamed>::", "", name))
     name = re.sub(r"^void ", "", name).split("(")[0]
-    if not re.search(r"gemm_tcgen05|mha_|cfm_attention|mixffn", name):
+    if not re.search(r"gemm_tcgen05|mha_|cfm_attention|mixffn|patch_embed", name):
         continue
     ops = re.findall(r"^\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", f, re.M)
     c = collections.Counter()
