@@ -20,7 +20,7 @@ def load(path):
 
 
 def last_step(ks):
-    starts = [i for i, d in enumerate(ks) if "im2col_nchw" in d["name"] or "patch_embed_s1" in d["name"]]
+    starts = [i for i, d in enumerate(ks) if "im2col_nchw" in d["name"] or "patch_embed" in d["name"]]
     return ks[starts[-1]:]
 
 

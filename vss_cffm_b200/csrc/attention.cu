@@ -142,16 +142,8 @@ mha_small_kv_kernel(const __half* __restrict__ q, int64_t ldq, const __half* __r
 }
 
 constexpr int SMEM_CAP = 200 * 1024;
-// Raises the dynamic shared-memory cap of `kernel` once per process (never inside a later stream capture).
-template <auto Kernel>                                          // one static per kernel, not per signature
-int set_smem_attr() {
-  static cudaError_t err = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP);
-  if (err != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(%d bytes): %s", SMEM_CAP, cudaGetErrorString(err));
-    return -(int)err;
-  }
-  return CFFM_OK;
-}
+template <auto Kernel>
+int set_smem_attr() { return set_dyn_smem<Kernel>(SMEM_CAP, "mha"); }
 
 }  // namespace
 }  // namespace cffm

@@ -609,9 +609,7 @@ cfm_attention_tc_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_co
 }
 
 int launch_cfm(const CUtensorMap* tm, const CfmParams& p, cudaStream_t st) {
-  static cudaError_t attr_err =
-      cudaFuncSetAttribute(cfm_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CFM_SMEM);
-  CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute(%d bytes): %s", CFM_SMEM, cudaGetErrorString(attr_err));
+  if (const int rc = set_dyn_smem<cfm_attention_tc_kernel>(CFM_SMEM, "cfm_attention")) return rc;
   // persistent CTAs, each bound to one head pair (its bias slice stays in shared memory) and walking over (clip, window) items
   const int n_items = p.B * p.nWh * p.nWw;
   int nslots = num_sms() / 4;

@@ -65,6 +65,23 @@ int make_tmap_4d(struct CUtensorMap_st* tm, const void* base, const int64_t dims
 int make_tmap_f32_4d(struct CUtensorMap_st* tm, const void* base, const int64_t dims[4], const int64_t strides[3], const int box[4]);
 int num_sms();
 
+// Raises the dynamic shared-memory cap of `Kernel` once per DEVICE (the attribute belongs to the kernel's per-device
+// function state; a process that drives several GPUs must set it on each).  One flag word per kernel instantiation.
+template <auto Kernel>
+inline int set_dyn_smem(int bytes, const char* what) {
+  static unsigned long long done = 0ull;                       // bit d: set on device d (benign race: the call is idempotent)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) dev = 63;
+  if ((done >> dev) & 1ull) return CFFM_OK;
+  const cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%d bytes): %s", what, bytes, cudaGetErrorString(e));
+    return -(int)e;
+  }
+  if (dev < 63) done |= 1ull << dev;
+  return CFFM_OK;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)) (nn.GELU() default), with

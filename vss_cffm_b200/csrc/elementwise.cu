@@ -1022,8 +1022,7 @@ extern "C" int cffm_im2col(const void* x, int layout, int N, int H, int W, int C
     CFFM_REQUIRE(smem <= 200 * 1024 && aligned16(A), CFFM_E_UNSUPPORTED,
                  "im2col: NCHW path stages C*k*(W+2*pad) halves (%d bytes) in shared memory", smem);
     CFFM_REQUIRE(aligned16(x), CFFM_E_BADARG, "im2col: misaligned input");
-    static cudaError_t e = cudaFuncSetAttribute(im2col_nchw_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    CFFM_REQUIRE(e == cudaSuccess, -(int)e, "im2col: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (const int rc = set_dyn_smem<im2col_nchw_f32_kernel>(200 * 1024, "im2col")) return rc;
     launch_k(im2col_nchw_f32_kernel, N * Ho, 256, smem, st, static_cast<const float*>(x), N, H, W, C, k, stride, pad, Ho, Wo,
                                                        static_cast<__half*>(A), Kpad);
   }
@@ -1214,8 +1213,7 @@ extern "C" int cffm_upsample2_argmax(const float* scores, int64_t ldc, int64_t* 
                need_y, need_x, UP_MT);
   const int smem = UP_MT * UP_MT * (ncls | 1) * 4;
   CFFM_REQUIRE(smem <= 200 * 1024, CFFM_E_UNSUPPORTED, "upsample2_argmax: too many classes (%d)", ncls);
-  static cudaError_t e = cudaFuncSetAttribute(upsample2_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  CFFM_REQUIRE(e == cudaSuccess, -(int)e, "upsample2_argmax: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  if (const int rc = set_dyn_smem<upsample2_argmax_kernel>(200 * 1024, "upsample2_argmax")) return rc;
   dim3 grid((Wo + UP_TILE - 1) / UP_TILE, (Ho + UP_TILE - 1) / UP_TILE, B);
   launch_k(upsample2_argmax_kernel, grid, 256, smem, static_cast<cudaStream_t>(stream), scores, ldc, labels, h, w, ncls, Hm, Wm, Ho, Wo);
   return launch_status("upsample2_argmax_kernel");

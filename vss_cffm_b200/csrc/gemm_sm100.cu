@@ -505,13 +505,14 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int num_sms() {   // shared: common.cuh
-  static int n = 0;
+int num_sms() {   // shared: common.cuh.  SM count of the CURRENT device (cached per device)
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) dev = 0;
+  int n = cache[dev];
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
   }
   return n;
 }
@@ -653,13 +654,7 @@ int launch_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, const
     rc = make_tmap_out(&tmO, ep.out16, M, N, ep.ldo16);
     if (rc) return rc;
   }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, F16_ONLY, LN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    C::SMEM_BYTES);
-  });
-  CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  if ((rc = set_dyn_smem<gemm_tcgen05_kernel<BN, F16_ONLY, LN, EW>>(C::SMEM_BYTES, "gemm"))) return rc;
   const int tiles_n = (N + BN - 1) / BN, tiles_m = cv != nullptr ? cv->n * cv->tiles_y : (M + BLOCK_M - 1) / BLOCK_M;
   const int tiles = tiles_n * tiles_m * ep.splits;
   const int slots = num_sms() * C::MIN_CTAS;

@@ -506,9 +506,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
 template <int OC, bool PAIR>
 int launch_mha(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const MhaParams& p, cudaStream_t st) {
-  static cudaError_t attr_err =
-      cudaFuncSetAttribute(mha_tc_kernel<OC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MHA);
-  CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute(%d bytes): %s", SMEM_MHA, cudaGetErrorString(attr_err));
+  if (const int rc = set_dyn_smem<mha_tc_kernel<OC, PAIR>>(SMEM_MHA, "mha")) return rc;
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
   launch_k(mha_tc_kernel<OC, PAIR>, grid, MHA_THREADS, SMEM_MHA, st, tmQ, tmK, tmV, p);
   return launch_status("mha_tc_kernel");

@@ -315,9 +315,7 @@ mixffn_tail_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
 
 template <int N>
 int launch_ffn(const CUtensorMap& tmH, const CUtensorMap& tmW, const FfnParams& p, cudaStream_t st) {
-  static cudaError_t attr_err =
-      cudaFuncSetAttribute(mixffn_tail_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<N>::SMEM);
-  CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute(%d bytes): %s", FfnCfg<N>::SMEM, cudaGetErrorString(attr_err));
+  if (const int rc = set_dyn_smem<mixffn_tail_kernel<N>>(FfnCfg<N>::SMEM, "mixffn_tail")) return rc;
   const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
   launch_k(mixffn_tail_kernel<N>, grid, FFN_THREADS, FfnCfg<N>::SMEM, st, tmH, tmW, p);
   return launch_status("mixffn_tail_kernel");

@@ -282,9 +282,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
 template <int N>
 int launch_pe(const CUtensorMap& tmX, const CUtensorMap& tmW, const PeParams& p, cudaStream_t st) {
-  static cudaError_t attr_err =
-      cudaFuncSetAttribute(patch_embed_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, PeCfg<N>::SMEM);
-  CFFM_REQUIRE(attr_err == cudaSuccess, -(int)attr_err, "cudaFuncSetAttribute(%d bytes): %s", PeCfg<N>::SMEM, cudaGetErrorString(attr_err));
+  if (const int rc = set_dyn_smem<patch_embed_kernel<N>>(PeCfg<N>::SMEM, "patch_embed_s1")) return rc;
   const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
   launch_k(patch_embed_kernel<N>, grid, PE_THREADS, PeCfg<N>::SMEM, st, tmX, tmW, p);
   return launch_status("patch_embed_kernel");
