@@ -161,6 +161,8 @@ class MixVisionTransformer(nn.Module):
             wp[:, :kdim] = w.permute(0, 2, 3, 1).reshape(cout, kdim).to(dev, _H)
             st = dict(k=k, stride=pe.stride, pad=k // 2, cin=cin, cout=cout, kpad=kpad, w=wp, b=f(pe.proj.bias),
                       ng=f(pe.norm.weight), nb=f(pe.norm.bias), eps=pe.norm.eps, blocks=[])
+            if (cin, k) == (3, 7):                               # stage 1: weight layout of the fused patch-embedding kernel
+                st["wk"] = ops.patch_embed_s1_weight(w.to(dev))
             for blk in getattr(self, f"block{s + 1}"):
                 a, m = blk.attn, blk.mlp
                 b = dict(n1g=f(blk.norm1.weight), n1b=f(blk.norm1.bias), n1eps=blk.norm1.eps,
@@ -208,11 +210,9 @@ class MixVisionTransformer(nn.Module):
             # fill = zero padding) whenever the image is fp16 NHWC with C % 64 == 0 (stages 2-4); the fp32 NCHW input frames
             # of stage 1 (3 channels) go through a patch matrix.
             implicit = layout == 1 and ops.conv_gemm_supported(st["cin"], Wo, stride) and (S > 1 or C <= 128)
-            fused_pe = layout == 0 and _PE_FUSED and ops.patch_embed_s1_supported(W, st["cin"], k, stride, pad, C)
+            fused_pe = layout == 0 and _PE_FUSED and "wk" in st and ops.patch_embed_s1_supported(W, st["cin"], k, stride, pad, C)
             if fused_pe:
                 # stage 1: convolution of the fp32 NCHW frames, both norms, one kernel, no patch matrix (csrc/patch_embed_sm100.cu)
-                if "wk" not in st:
-                    st["wk"] = ops.patch_embed_s1_weight(self.patch_embed1.proj.weight)
                 ops.patch_embed_s1(cur, st["wk"], st["b"], st["ng"], st["nb"], st["eps"], b0["n1g"], b0["n1b"], b0["n1eps"], xres, xn)
             elif not implicit:
                 col = ws.get(f"s{s}.col", (M, st["kpad"]), _H)
