@@ -348,9 +348,47 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     n0 = _abi.n_launches
-    total_ms = timed(step_dev, args.steps)
+    serial_ms = timed(step_dev, args.steps)                      # one pass at a time: per-step events, flush outside them
     launches = _abi.n_launches - n0
     barrier()
+    total_ms, passes_in_flight = serial_ms, 1
+    if graphed is not None and not frames_mode:
+        # Headline: K steps as TWO passes in flight.  Each pass is one CUDA-graph replay over its OWN intermediate buffers on its
+        # own stream (the weights are shared, read-only), so the kernels of consecutive batches interleave on the GPU: a pass is a
+        # dependent chain of ~110 kernels, most of them small, and one chain's bubbles are filled by the other.  The L2 flush of
+        # every step runs INSIDE the timed region, on the step's stream.
+        from vss_cffm_b200.graph import GraphedClips
+        slots = [GraphedClips(model, B, T, H, W, metas, True, head_kw, warmup=2, private_input=True, private_workspace=True)
+                 for _ in range(2)]
+        slots[0].load(imgs_dev)
+        slots[1].load([t.cuda() for t in synth.synth_clip(B, T, H, W, seed=300 + rank)])
+        lanes = [torch.cuda.Stream() for _ in slots]
+        chk0 = slots[0].replay().clone()
+        torch.cuda.synchronize()
+        assert torch.equal(chk0, model.predict_labels(imgs_dev, metas, **head_kw)), "private-workspace graph differs from the direct call"
+
+        def pipelined_dev(steps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for st in lanes:
+                st.wait_event(e0)
+            for i in range(steps):
+                with torch.cuda.stream(lanes[i & 1]):
+                    flush.fill_(1)
+                    slots[i & 1].replay()
+            for st in lanes:
+                torch.cuda.current_stream().wait_stream(st)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1)
+
+        pipelined_dev(4)
+        barrier()
+        n0 = _abi.n_launches
+        total_ms, passes_in_flight = pipelined_dev(args.steps), 2
+        launches = _abi.n_launches - n0
+        barrier()
     clocks = sampler.stop() if sampler else None
 
     for _ in range(3):
@@ -465,11 +503,11 @@ def main():
     # global batch spread over the ranks, one NCCL all-gather of the reference-frame K/V per step (vss_cffm_b200/parallel.py)
     frame_shard = None
     if world > 1 and not frames_mode and T == 4 and KIND == "cffm":
-        frame_shard = measure_frame_shard(args, model, rank, world, B, flush, total_ms)
-    t = torch.tensor([total_ms, e2e_ms, e2e_serial_ms, e2e_u8_ms], dtype=torch.float64, device="cuda")
+        frame_shard = measure_frame_shard(args, model, rank, world, B, flush, serial_ms)   # like with like: one pass at a time
+    t = torch.tensor([total_ms, e2e_ms, e2e_serial_ms, e2e_u8_ms, serial_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, e2e_serial_ms, e2e_u8_ms = t.tolist()
+    total_ms, e2e_ms, e2e_serial_ms, e2e_u8_ms, serial_ms = t.tolist()
     frames = B * T * n_gpus * args.steps
     value = frames / (total_ms * 1e-3)
     e2e_value = frames / (e2e_ms * 1e-3)
@@ -555,7 +593,12 @@ def main():
                                     " (BASELINE configs[3])" if (VARIANT, KIND, T) == ("b2", "cffm", 4) else
                                     " (BASELINE configs[4])" if (VARIANT, KIND, PROTOS) == ("b1", "cffmpp", 64) else ""),
                        "clips_per_gpu": B, "frames_per_step": B * T * n_gpus, "shard": args.shard if n_gpus > 1 else "none",
-                       "l2": "256 MiB flush between timed steps", "timing": "per-step CUDA events, max over ranks"},
+                       "l2": "256 MiB flush per step" + (", inside the timed region (on the step's stream)" if passes_in_flight == 2 else ", between the per-step events"),
+                       "timing": ("K steps as 2 passes in flight (one CUDA-graph replay each, own buffers, own stream), one CUDA-event pair around "
+                                  "all K, max over ranks" if passes_in_flight == 2 else "per-step CUDA events, max over ranks"),
+                       "passes_in_flight": passes_in_flight},
+            "single_pass": {"value": round(frames / (serial_ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(serial_ms / args.steps, 4),
+                            "timing": "one pass at a time: per-step CUDA events, L2 flush between them (the round-1 definition of `value`)"},
             "clocks": clocks,
             "e2e": e2e_main,
             "e2e_from_fp32_tensors": e2e_fp32 if e2e_u8 else None,

@@ -10,9 +10,12 @@ from . import _abi
 
 class GraphedClips:
     def __init__(self, model, B, T, H, W, img_meta=None, rescale=True, head_kw=None, warmup=3, private_input=False,
-                 preprocessor=None, src_hw=None):
+                 preprocessor=None, src_hw=None, private_workspace=False):
         """``preprocessor`` (a ``ClipPreprocessor``) + ``src_hw``: the captured pass starts from a static uint8 BGR HWC
-        buffer ``self.frames_u8`` (T, B, h, w, 3) of decoded frames instead of the normalised fp32 frames."""
+        buffer ``self.frames_u8`` (T, B, h, w, 3) of decoded frames instead of the normalised fp32 frames.
+        ``private_workspace``: the pass is captured over its OWN intermediate buffers (the model's workspaces are swapped
+        for fresh ones during warm-up and capture), so two such graphs may replay CONCURRENTLY on different streams; the
+        weights (plans) stay shared, they are read-only."""
         dev = model._device()
         if dev.type != "cuda":
             raise _abi.CffmError("CUDA graphs need the model on a CUDA device")
@@ -35,20 +38,32 @@ class GraphedClips:
                 preprocessor.run(self.frames_u8.view(T * B, *self.frames_u8.shape[2:]), T, B, out=self.frames)
             return model.labels_from_frames(self.frames, self.meta, rescale, **head_kw)
 
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):                            # plans, workspaces, func attributes: all set here
-            for _ in range(warmup):
-                run_pass()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = _abi.n_launches
-        with torch.cuda.graph(self.graph):
-            self.labels = run_pass()
-        self.kernels_per_replay = _abi.n_launches - n0
-        for ws in model.workspaces():                            # the graph replays on these addresses: never free them
-            ws.pin()
+        saved = []
+        if private_workspace:
+            from .workspace import Workspace
+            for owner in (model, model.backbone, model.decode_head):
+                if hasattr(owner, "_ws"):
+                    saved.append((owner, owner._ws))
+                    owner._ws = Workspace()
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                        # plans, workspaces, func attributes: all set here
+                for _ in range(warmup):
+                    run_pass()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = _abi.n_launches
+            with torch.cuda.graph(self.graph):
+                self.labels = run_pass()
+            self.kernels_per_replay = _abi.n_launches - n0
+            self._workspaces = list(model.workspaces())
+            for ws in self._workspaces:                          # the graph replays on these addresses: never free them
+                ws.pin()
+        finally:
+            for owner, ws in saved:
+                owner._ws = ws
         # ... and on the folded weights of the plans it was captured with: keep them alive even if a later
         # load_state_dict() rebuilds the plans (the owner is expected to drop this graph then: invalidate_graphs())
         self._plans = (getattr(model.backbone, "_plan", None), getattr(model.decode_head, "_plan", None))
@@ -73,8 +88,11 @@ class GraphedClips:
 class ClipPipeline:
     """Streaming inference from HOST buffers: the H2D copy of clip batch i+1 and the D2H read of the labels of
     batch i-1 overlap the kernels of batch i.  ``depth`` graph instances (one static input buffer and one label
-    buffer each, shared workspace) rotate; three streams (copy-in, compute, copy-out) are ordered with events only,
-    so ``submit`` never blocks the host unless all slots are in flight.
+    buffer each, OWN workspace) rotate; the streams (copy-in, one compute stream PER SLOT, copy-out) are ordered with events
+    only, so ``submit`` never blocks the host unless all slots are in flight.  Because every slot owns its intermediate
+    buffers, the passes of consecutive batches also overlap ON the GPU: a pass is a dependent chain of ~110 kernels, most of
+    them small, and the bubbles of one chain (launch-to-launch latency, tiles that fill a fraction of the SMs) are filled by
+    the other (+19 % throughput with two passes in flight, tools/overlap_probe.py).
 
         pipe = ClipPipeline(model, B, T, H, W)
         tickets = [pipe.submit(frames_host[i], labels_host[i]) for i in ...]   # pinned host tensors
@@ -89,18 +107,21 @@ class ClipPipeline:
         self.slots = []
         for s in range(depth):
             g = GraphedClips(model, B, T, H, W, img_meta, rescale, head_kw, warmup=3 if s == 0 else 1, private_input=True,
-                             preprocessor=preprocessor, src_hw=src_hw)
-            self.slots.append(dict(g=g, h2d=torch.cuda.Event(), done=torch.cuda.Event(), d2h=torch.cuda.Event(), used=False))
-        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+                             preprocessor=preprocessor, src_hw=src_hw, private_workspace=True)
+            self.slots.append(dict(g=g, h2d=torch.cuda.Event(), done=torch.cuda.Event(), d2h=torch.cuda.Event(), used=False,
+                                   run=torch.cuda.Stream(device=dev)))
+        self.s_in, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(2))
         self.n = 0
 
     @property
     def compute_stream(self):
-        return self.s_run
+        """Compute stream of the slot the NEXT submit will use."""
+        return self.slots[self.n % self.depth]["run"]
 
     def submit(self, imgs, labels_host):
         """imgs: list of T (B,3,H,W) pinned host tensors (or one (T,B,3,H,W)); labels_host: pinned int64 (B,H,W)."""
         sl = self.slots[self.n % self.depth]
+        s_run = sl["run"]
         g = sl["g"]
         with torch.cuda.stream(self.s_in):
             if sl["used"]:
@@ -112,12 +133,12 @@ class ClipPipeline:
             else:
                 dst.copy_(imgs, non_blocking=True)
             sl["h2d"].record(self.s_in)
-        with torch.cuda.stream(self.s_run):
-            self.s_run.wait_event(sl["h2d"])
+        with torch.cuda.stream(s_run):
+            s_run.wait_event(sl["h2d"])
             if sl["used"]:
-                self.s_run.wait_event(sl["d2h"])                 # its label buffer has been read back
+                s_run.wait_event(sl["d2h"])                      # its label buffer has been read back
             g.replay()
-            sl["done"].record(self.s_run)
+            sl["done"].record(s_run)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(sl["done"])
             labels_host.copy_(g.labels, non_blocking=True)
