@@ -296,6 +296,31 @@ def test_cuda_graph_replay_equals_eager(full_model):
         assert torch.equal(eager, graphed)
 
 
+def test_two_passes_in_flight_on_private_workspaces(full_model):
+    """Two captured passes that own their intermediate buffers replay CONCURRENTLY on two streams (bench.py's headline mode,
+    ClipPipeline's slots) and each reproduces the eager labels of its own clip batch; the model's own workspaces are untouched."""
+    from vss_cffm_b200.graph import GraphedClips
+    m = full_model
+    metas = synth.img_metas(2, 480, 480)
+    ws_before = [id(w) for w in m.workspaces()]
+    clips = [synth.synth_clip(2, 4, 480, 480, seed=s) for s in (31, 32)]
+    eager = [m.predict_labels(c, metas).clone() for c in clips]
+    graphs = [GraphedClips(m, 2, 4, 480, 480, metas, warmup=2, private_input=True, private_workspace=True) for _ in clips]
+    assert [id(w) for w in m.workspaces()] == ws_before
+    for g, c in zip(graphs, clips):
+        g.load([t.cuda() for t in c])
+    lanes = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rep in range(6):                                          # interleaved replays, no ordering between the two lanes
+        for g, st in zip(graphs, lanes):
+            with torch.cuda.stream(st):
+                g.replay()
+    torch.cuda.synchronize()
+    for g, e in zip(graphs, eager):
+        assert torch.equal(g.labels, e)
+    assert torch.equal(m.predict_labels(clips[0], metas), eager[0])   # the shared-workspace path still works beside them
+
+
 def test_mmseg_call_replays_a_cached_graph():
     """``model(img=..., return_loss=False)`` -- the reference-facing call -- captures the pass on the second call with the
     same geometry and replays it afterwards; labels are bit-identical to the eager path, also across geometries and after
