@@ -435,14 +435,21 @@ def main():
         # the headline e2e (whose input is the fp32 tensor the reference model itself receives).
         from vss_cffm_b200.preprocess import ClipPreprocessor
         pre = ClipPreprocessor()
-        pipe = ClipPipeline(model, B, T, H, W, metas, head_kw=head_kw, preprocessor=pre, src_hw=(H, W))
+        # ... and 8-bit label maps back (124 classes): an eighth of the D2H bytes; the values are the int64 labels' (checked below)
+        pipe = ClipPipeline(model, B, T, H, W, metas, head_kw=dict(head_kw, label_dtype=torch.uint8), preprocessor=pre, src_hw=(H, W))
         g8 = torch.Generator().manual_seed(300 + rank)
         hosts = [torch.randint(0, 256, (T, B, H, W, 3), dtype=torch.uint8, generator=g8).pin_memory() for _ in range(3)]
+        labs = [torch.empty(B, H, W, dtype=torch.uint8).pin_memory() for _ in range(3)]
         pipelined(3)
+        fr = pre.run(hosts[2].cuda().view(T * B, H, W, 3), T, B)
+        chk = model.labels_from_frames(fr, metas, **head_kw)
+        torch.cuda.synchronize()
+        assert torch.equal(chk.cpu().to(torch.uint8), labs[2]), "uint8 pipeline labels differ from the int64 labels of the direct call"
         u8_ms = pipelined(args.steps)
         e2e_u8 = {"value": None, "unit": UNIT, "ms_per_step": round(u8_ms / args.steps, 4), "h2d_bytes_per_step": B * T * 3 * H * W,
-                  "d2h_bytes_per_step": B * H * W * 8,
-                  "api": "ClipPipeline(preprocessor=ClipPreprocessor()).submit(pinned uint8 BGR HWC frames, pinned labels)"}
+                  "d2h_bytes_per_step": B * H * W,
+                  "api": "ClipPipeline(preprocessor=ClipPreprocessor(), head_kw={'label_dtype': torch.uint8}).submit(pinned uint8 BGR HWC "
+                         "frames, pinned uint8 labels)"}
         e2e_u8_ms = u8_ms
         barrier()
 

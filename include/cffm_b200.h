@@ -291,6 +291,9 @@ int cffm_resize_argmax(const float* logits, int64_t* labels, int B, int ncls, in
  * cffm_resize_argmax). */
 int cffm_upsample2_argmax(const float* scores, int64_t ldc, int64_t* labels, int B, int h, int w,
                           int ncls, int Hm, int Wm, int Ho, int Wo, void* stream);
+/* The same with 8-bit labels (ncls <= 256): an eighth of the bytes that leave the device per step. */
+int cffm_upsample2_argmax_u8(const float* scores, int64_t ldc, uint8_t* labels, int B, int h, int w,
+                             int ncls, int Hm, int Wm, int Ho, int Wo, void* stream);
 
 /* Bilinear (align_corners=False) resize of fp32 NCHW maps [B,C,h,w] -> [B,C,Ho,Wo]: the extra
  * "rescale to ori_shape" step of whole_inference (encoder_decoder.py:507-514). */

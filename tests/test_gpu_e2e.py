@@ -296,6 +296,16 @@ def test_cuda_graph_replay_equals_eager(full_model):
         assert torch.equal(eager, graphed)
 
 
+def test_uint8_labels_equal_int64_labels(full_model):
+    """``label_dtype=torch.uint8`` (an eighth of the bytes read back per step) carries the same label values."""
+    m = full_model
+    metas = synth.img_metas(2, 480, 480)
+    imgs = synth.synth_clip(2, 4, 480, 480, seed=33)
+    a = m.predict_labels(imgs, metas)
+    b = m.predict_labels(imgs, metas, label_dtype=torch.uint8)
+    assert a.dtype == torch.int64 and b.dtype == torch.uint8 and torch.equal(a, b.to(torch.int64))
+
+
 def test_two_passes_in_flight_on_private_workspaces(full_model):
     """Two captured passes that own their intermediate buffers replay CONCURRENTLY on two streams (bench.py's headline mode,
     ClipPipeline's slots) and each reproduces the eager labels of its own clip batch; the model's own workspaces are untouched."""

@@ -64,6 +64,7 @@ SIGNATURES = {
     "cffm_resize_nhwc_to_nchw": ([vp, i32, i64, vp, i32, i32, i32, i32, i32, i32, vp], i32),
     "cffm_resize_argmax": ([vp, vp, i32, i32, i32, i32, i32, i32, vp], i32),
     "cffm_upsample2_argmax": ([vp, i64, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
+    "cffm_upsample2_argmax_u8": ([vp, i64, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
     "cffm_resize_nchw": ([vp, vp, i32, i32, i32, i32, i32, i32, vp], i32),
     "cffm_softmax_nchw": ([vp, vp, i32, i32, i64, vp], i32),
 }

@@ -814,8 +814,9 @@ softmax_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int B
 // values it needs are computed once per class into shared memory from the low-resolution map
 // (channel-contiguous = coalesced reads), then every thread scans the classes of its own pixel.
 constexpr int UP_TILE = 16, UP_MT = 8;
+template <typename LT>                                          // label type: int64_t (what argmax returns) or uint8_t (ncls <= 256)
 __global__ void __launch_bounds__(256)
-upsample2_argmax_kernel(const float* __restrict__ lg, int64_t ldc, int64_t* __restrict__ labels, int h, int w,
+upsample2_argmax_kernel(const float* __restrict__ lg, int64_t ldc, LT* __restrict__ labels, int h, int w,
                         int ncls, int Hm, int Wm, int Ho, int Wo) {
   pdl_sync();
   extern __shared__ __align__(16) uint8_t up_smem[];
@@ -849,7 +850,7 @@ upsample2_argmax_kernel(const float* __restrict__ lg, int64_t ldc, int64_t* __re
     const float v = ly.w0 * (lx.w0 * p00[c] + lx.w1 * p01[c]) + ly.w1 * (lx.w0 * p10[c] + lx.w1 * p11[c]);
     if (v > best) { best = v; arg = c; }
   }
-  labels[(static_cast<int64_t>(b) * Ho + Y) * Wo + X] = arg;
+  labels[(static_cast<int64_t>(b) * Ho + Y) * Wo + X] = static_cast<LT>(arg);
 }
 
 // Fast path of the same operation for the production geometry: exact x2 (h -> 2h) followed by exact x4 (2h -> 8h).
@@ -862,8 +863,9 @@ upsample2_argmax_kernel(const float* __restrict__ lg, int64_t ldc, int64_t* __re
 // Same interpolation formula and operand order as the generic kernels; the 4 partial winners of a pixel are merged
 // with "greater, or equal and lower class index" so the result is the first maximum, like argmax.
 constexpr int UQ_CELLS = 8, UQ_MID = UQ_CELLS + 1, UQ_PITCH = 132;
+template <typename LT>
 __global__ void __launch_bounds__(256)
-upsample2x4_argmax_kernel(const float* __restrict__ lg, int64_t ldc, int64_t* __restrict__ labels, int h, int w, int ncls) {
+upsample2x4_argmax_kernel(const float* __restrict__ lg, int64_t ldc, LT* __restrict__ labels, int h, int w, int ncls) {
   pdl_sync();
   __shared__ __align__(16) float mid[UQ_MID * UQ_MID * UQ_PITCH];
   const int Hm = 2 * h, Wm = 2 * w, Ho = 8 * h, Wo = 8 * w;
@@ -941,11 +943,11 @@ upsample2x4_argmax_kernel(const float* __restrict__ lg, int64_t ldc, int64_t* __
   for (int j = 0; j < 4; ++j) rowv[j] = g == 0 ? arg[j] : (g == 1 ? arg[4 + j] : (g == 2 ? arg[8 + j] : arg[12 + j]));
   const int Y = Yb + g;
   if (Y >= 0 && Y < Ho) {
-    int64_t* orow = labels + (static_cast<int64_t>(b) * Ho + Y) * Wo;
+    LT* orow = labels + (static_cast<int64_t>(b) * Ho + Y) * Wo;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int X = Xb + j;
-      if (X >= 0 && X < Wo) orow[X] = rowv[j];
+      if (X >= 0 && X < Wo) orow[X] = static_cast<LT>(rowv[j]);
     }
   }
 }
@@ -1194,16 +1196,20 @@ extern "C" int cffm_softmax_nchw(const float* in, float* out, int B, int C, int6
   return launch_status("softmax_nchw_kernel");
 }
 
-extern "C" int cffm_upsample2_argmax(const float* scores, int64_t ldc, int64_t* labels, int B, int h, int w, int ncls,
-                                     int Hm, int Wm, int Ho, int Wo, void* stream) {
+namespace cffm {
+namespace {
+template <typename LT>
+int upsample2_argmax_impl(const float* scores, int64_t ldc, LT* labels, int B, int h, int w, int ncls, int Hm, int Wm, int Ho,
+                          int Wo, void* stream) {
   CFFM_REQUIRE(scores && labels, CFFM_E_BADARG, "upsample2_argmax: null pointer");
   CFFM_REQUIRE(B > 0 && h > 0 && w > 0 && ncls > 0 && Hm > 0 && Wm > 0 && Ho > 0 && Wo > 0 && ldc >= ncls && B <= 65535,
                CFFM_E_BADARG, "upsample2_argmax: bad size");
+  CFFM_REQUIRE(sizeof(LT) > 1 || ncls <= 256, CFFM_E_UNSUPPORTED, "upsample2_argmax: %d classes do not fit 8-bit labels", ncls);
   if (Hm == 2 * h && Wm == 2 * w && Ho == 4 * Hm && Wo == 4 * Wm && ncls <= 128 && ldc % 4 == 0 && ldc >= (ncls + 3) / 4 * 4 &&
       aligned16(scores)) {
     // cells cy = -1 .. Hm - 1 (the first / last ones are half outside the image)
     dim3 grid((Wm + 1 + UQ_CELLS - 1) / UQ_CELLS, (Hm + 1 + UQ_CELLS - 1) / UQ_CELLS, B);
-    launch_k(upsample2x4_argmax_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), scores, ldc, labels, h, w, ncls);
+    launch_k(upsample2x4_argmax_kernel<LT>, grid, 256, 0, static_cast<cudaStream_t>(stream), scores, ldc, labels, h, w, ncls);
     return launch_status("upsample2x4_argmax_kernel");
   }
   // intermediate rows/cols touched by a 16-pixel output tile: 16 * Hm/Ho + 3 (two taps + rounding)
@@ -1213,10 +1219,22 @@ extern "C" int cffm_upsample2_argmax(const float* scores, int64_t ldc, int64_t* 
                need_y, need_x, UP_MT);
   const int smem = UP_MT * UP_MT * (ncls | 1) * 4;
   CFFM_REQUIRE(smem <= 200 * 1024, CFFM_E_UNSUPPORTED, "upsample2_argmax: too many classes (%d)", ncls);
-  if (const int rc = set_dyn_smem<upsample2_argmax_kernel>(200 * 1024, "upsample2_argmax")) return rc;
+  if (const int rc = set_dyn_smem<upsample2_argmax_kernel<LT>>(200 * 1024, "upsample2_argmax")) return rc;
   dim3 grid((Wo + UP_TILE - 1) / UP_TILE, (Ho + UP_TILE - 1) / UP_TILE, B);
-  launch_k(upsample2_argmax_kernel, grid, 256, smem, static_cast<cudaStream_t>(stream), scores, ldc, labels, h, w, ncls, Hm, Wm, Ho, Wo);
+  launch_k(upsample2_argmax_kernel<LT>, grid, 256, smem, static_cast<cudaStream_t>(stream), scores, ldc, labels, h, w, ncls, Hm, Wm, Ho, Wo);
   return launch_status("upsample2_argmax_kernel");
+}
+}  // namespace
+}  // namespace cffm
+
+extern "C" int cffm_upsample2_argmax(const float* scores, int64_t ldc, int64_t* labels, int B, int h, int w, int ncls,
+                                     int Hm, int Wm, int Ho, int Wo, void* stream) {
+  return cffm::upsample2_argmax_impl<int64_t>(scores, ldc, labels, B, h, w, ncls, Hm, Wm, Ho, Wo, stream);
+}
+
+extern "C" int cffm_upsample2_argmax_u8(const float* scores, int64_t ldc, uint8_t* labels, int B, int h, int w, int ncls,
+                                        int Hm, int Wm, int Ho, int Wo, void* stream) {
+  return cffm::upsample2_argmax_impl<uint8_t>(scores, ldc, labels, B, h, w, ncls, Hm, Wm, Ho, Wo, stream);
 }
 
 extern "C" int cffm_layernorm_sum(const float* partials, int nsum, const float* bias, const float* gamma, const float* beta,

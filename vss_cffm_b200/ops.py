@@ -385,11 +385,12 @@ def resize_argmax(logits, labels, B, ncls, h, w, Ho, Wo):
 
 
 def upsample2_argmax(scores, ncls, labels, B, h, w, Hm, Wm, Ho, Wo):
-    """scores fp32 [B*h*w, ldc] NHWC -> two chained bilinear resizes -> argmax labels int64 [B,Ho,Wo]."""
+    """scores fp32 [B*h*w, ldc] NHWC -> two chained bilinear resizes -> argmax labels [B,Ho,Wo], int64 or uint8 (ncls <= 256)."""
     _chk(scores, _F, "upsample2_argmax.scores")
     assert scores.dim() == 2 and scores.shape[0] == B * h * w and scores.shape[1] >= ncls
-    assert labels.dtype == torch.int64 and labels.is_cuda and labels.is_contiguous() and labels.numel() == B * Ho * Wo
-    _abi.call("cffm_upsample2_argmax", _ptr(scores), _ld(scores), _ptr(labels), B, h, w, ncls, Hm, Wm, Ho, Wo, _stream())
+    assert labels.dtype in (torch.int64, torch.uint8) and labels.is_cuda and labels.is_contiguous() and labels.numel() == B * Ho * Wo
+    _abi.call("cffm_upsample2_argmax" if labels.dtype == torch.int64 else "cffm_upsample2_argmax_u8", _ptr(scores), _ld(scores),
+              _ptr(labels), B, h, w, ncls, Hm, Wm, Ho, Wo, _stream())
 
 
 def upsample2_argmax_supported(Hm, Wm, Ho, Wo):

@@ -193,9 +193,11 @@ class EncoderDecoder_clips(nn.Module):
         frames, B, T = self._stack(img)
         return self.labels_from_frames(frames, img_meta, rescale, **head_kw)
 
-    def labels_from_frames(self, frames, img_meta, rescale=True, **head_kw):
-        """frames: (T,B,3,H,W) fp32 on the device, frame-major -> int64 labels (B,H,W).  Pure sequence of
-        C-ABI launches on the current stream (no host sync, stable workspace addresses): CUDA-graph capturable."""
+    def labels_from_frames(self, frames, img_meta, rescale=True, label_dtype=torch.int64, **head_kw):
+        """frames: (T,B,3,H,W) fp32 on the device, frame-major -> labels (B,H,W), int64 like the reference's argmax or
+        (``label_dtype=torch.uint8``, at most 256 classes) 8-bit: an eighth of the bytes a serving loop reads back.  Pure
+        sequence of C-ABI launches on the current stream (no host sync, stable workspace addresses): CUDA-graph capturable."""
+        assert label_dtype in (torch.int64, torch.uint8) and (label_dtype == torch.int64 or self.num_classes <= 256)
         T, B = frames.shape[:2]
         H, W = frames.shape[-2:]
         ori = tuple(img_meta[0]["ori_shape"][:2])
@@ -208,7 +210,7 @@ class EncoderDecoder_clips(nn.Module):
                 head_kw = dict(head_kw, img_metas=img_meta)
             scores, (hs, ws_), (h, w) = head.forward_scores(x, B, t, frame_major=True, **head_kw)
             if ops.upsample2_argmax_supported(h, w, H, W):       # head's x2 resize + the x4 resize + argmax: one kernel
-                labels = torch.empty(B, H, W, dtype=torch.int64, device=scores.device)
+                labels = torch.empty(B, H, W, dtype=label_dtype, device=scores.device)
                 ops.upsample2_argmax(scores, self.num_classes, labels, B, hs, ws_, h, w, H, W)
                 return self._flip(labels, img_meta)
             logits = torch.empty(B, self.num_classes, h, w, dtype=_F, device=scores.device)
@@ -222,7 +224,7 @@ class EncoderDecoder_clips(nn.Module):
             logits, h, w, H, W = mid, H, W, ori[0], ori[1]
         labels = torch.empty(B, H, W, dtype=torch.int64, device=logits.device)
         ops.resize_argmax(logits, labels, B, self.num_classes, h, w, H, W)
-        return self._flip(labels, img_meta)
+        return self._flip(labels, img_meta).to(label_dtype)
 
     def make_graphed(self, B, T, H, W, img_meta=None, rescale=True, **head_kw):
         """Capture one inference pass for fixed (B,T,H,W) in a CUDA graph: the ~130 kernel launches of a step are
