@@ -332,6 +332,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    checks = {}
+
+    def check(name, ok):
+        """Bit-identity checks of the measured modes against the direct call: reported in the JSON line (a failed check must
+        not cost the whole line, it is printed loudly instead)."""
+        checks[name] = bool(ok)
+        if not ok:
+            print(f"rank {rank}: CHECK FAILED: {name}", file=sys.stderr)
+
     def timed(fn, steps):
         """Sum of per-step CUDA-event times; L2 is flushed between steps outside the events."""
         evs = []
@@ -365,7 +374,7 @@ def main():
         lanes = [torch.cuda.Stream() for _ in slots]
         chk0 = slots[0].replay().clone()
         torch.cuda.synchronize()
-        assert torch.equal(chk0, model.predict_labels(imgs_dev, metas, **head_kw)), "private-workspace graph differs from the direct call"
+        check("two_passes_in_flight_labels_equal_direct_call", torch.equal(chk0, model.predict_labels(imgs_dev, metas, **head_kw)))
 
         def pipelined_dev(steps):
             torch.cuda.synchronize()
@@ -424,7 +433,7 @@ def main():
         # the pipelined labels must be the labels of the plain call on the same frames
         chk = model.predict_labels(hosts[2], metas, **head_kw)
         torch.cuda.synchronize()
-        assert torch.equal(chk.cpu(), labs[2]), "pipelined labels differ from the direct call"
+        check("pipeline_labels_equal_direct_call", torch.equal(chk.cpu(), labs[2]))
         barrier()
         e2e_ms = pipelined(args.steps)
         e2e_api = ("ClipPipeline.submit(pinned host frames, pinned host labels): H2D / CUDA-graph replay / D2H on three "
@@ -444,7 +453,7 @@ def main():
         fr = pre.run(hosts[2].cuda().view(T * B, H, W, 3), T, B)
         chk = model.labels_from_frames(fr, metas, **head_kw)
         torch.cuda.synchronize()
-        assert torch.equal(chk.cpu().to(torch.uint8), labs[2]), "uint8 pipeline labels differ from the int64 labels of the direct call"
+        check("uint8_pipeline_labels_equal_int64_labels", torch.equal(chk.cpu().to(torch.uint8), labs[2]))
         u8_ms = pipelined(args.steps)
         e2e_u8 = {"value": None, "unit": UNIT, "ms_per_step": round(u8_ms / args.steps, 4), "h2d_bytes_per_step": B * T * 3 * H * W,
                   "d2h_bytes_per_step": B * H * W,
@@ -612,6 +621,7 @@ def main():
             "e2e_mmseg_call": mmseg_call,
             "streaming": (dict(streaming, stateless_equivalent=round(value / T, 2)) if streaming else None),
             "gpu_launches": launches,
+            "checks": checks,
             "launch_mode": (f"CUDA graph replay ({graphed.kernels_per_replay} kernel nodes per step)" if graphed is not None else
                             f"CUDA graph replay ({frames_graph_nodes} kernel nodes + 1 NCCL all-gather per step)" if frames_graph_nodes
                             else "eager"),
