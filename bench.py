@@ -366,38 +366,44 @@ def main():
         # own stream (the weights are shared, read-only), so the kernels of consecutive batches interleave on the GPU: a pass is a
         # dependent chain of ~110 kernels, most of them small, and one chain's bubbles are filled by the other.  The L2 flush of
         # every step runs INSIDE the timed region, on the step's stream.
-        from vss_cffm_b200.graph import GraphedClips
-        slots = [GraphedClips(model, B, T, H, W, metas, True, head_kw, warmup=2, private_input=True, private_workspace=True)
-                 for _ in range(2)]
-        slots[0].load(imgs_dev)
-        slots[1].load([t.cuda() for t in synth.synth_clip(B, T, H, W, seed=300 + rank)])
-        lanes = [torch.cuda.Stream() for _ in slots]
-        chk0 = slots[0].replay().clone()
-        torch.cuda.synchronize()
-        check("two_passes_in_flight_labels_equal_direct_call", torch.equal(chk0, model.predict_labels(imgs_dev, metas, **head_kw)))
-
-        def pipelined_dev(steps):
+        try:
+            from vss_cffm_b200.graph import GraphedClips
+            slots = [GraphedClips(model, B, T, H, W, metas, True, head_kw, warmup=2, private_input=True, private_workspace=True)
+                     for _ in range(2)]
+            slots[0].load(imgs_dev)
+            slots[1].load([t.cuda() for t in synth.synth_clip(B, T, H, W, seed=300 + rank)])
+            lanes = [torch.cuda.Stream() for _ in slots]
+            chk0 = slots[0].replay().clone()
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for st in lanes:
-                st.wait_event(e0)
-            for i in range(steps):
-                with torch.cuda.stream(lanes[i & 1]):
-                    flush.fill_(1)
-                    slots[i & 1].replay()
-            for st in lanes:
-                torch.cuda.current_stream().wait_stream(st)
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1)
+            check("two_passes_in_flight_labels_equal_direct_call", torch.equal(chk0, model.predict_labels(imgs_dev, metas, **head_kw)))
 
-        pipelined_dev(4)
-        barrier()
-        n0 = _abi.n_launches
-        total_ms, passes_in_flight = pipelined_dev(args.steps), 2
-        launches = _abi.n_launches - n0
-        barrier()
+            def pipelined_dev(steps):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for st in lanes:
+                    st.wait_event(e0)
+                for i in range(steps):
+                    with torch.cuda.stream(lanes[i & 1]):
+                        flush.fill_(1)
+                        slots[i & 1].replay()
+                for st in lanes:
+                    torch.cuda.current_stream().wait_stream(st)
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1)
+
+            pipelined_dev(4)
+            barrier()
+            n0 = _abi.n_launches
+            total_ms, passes_in_flight = pipelined_dev(args.steps), 2
+            launches = _abi.n_launches - n0
+            barrier()
+        except Exception as e:                                   # keep the single-pass number rather than lose the line
+            if world > 1:                                        # ... but never leave the other ranks waiting at a barrier
+                raise
+            print(f"rank {rank}: two passes in flight not measured ({type(e).__name__}: {e}); reporting one pass at a time", file=sys.stderr)
+            total_ms, passes_in_flight = serial_ms, 1
     clocks = sampler.stop() if sampler else None
 
     for _ in range(3):
