@@ -151,6 +151,23 @@ def cpu_reference_time(sd, steps, warmup, clips=1):
 def run_reference(args, rank):
     if rank != 0:
         return
+    if os.environ.get("OMP_NUM_THREADS") and not os.environ.get("CFFM_REF_CHILD"):
+        # torchrun pins OMP_NUM_THREADS=1 before the interpreter starts: the OpenMP pool of THIS process stays at one thread
+        # whatever torch.set_num_threads() says later.  The CPU arm must use every host core: re-run it in a clean child.
+        import subprocess
+        drop = ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK",
+                "ROLE_RANK", "ROLE_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")
+        env = {k: v for k, v in os.environ.items() if k not in drop and not k.startswith("TORCHELASTIC")}
+        env["CFFM_REF_CHILD"] = "1"
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", str(args.gpus), "--steps", str(args.steps),
+               "--warmup", str(args.warmup), "--variant", args.variant, "--clips", str(args.clips), "--T", str(args.T),
+               "--kind", args.kind, "--protos", str(args.protos)]
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if out.returncode == 0 and lines:
+            print(lines[-1])
+            return
+        print(f"reference child failed (rc {out.returncode}): {out.stderr[-400:]}; timing in-process", file=sys.stderr)
     _, sd = oracle_state()
     steps = max(1, min(args.steps, 8))                       # bounded: ~2 s per clip on 8 cores
     value, ms, cores = cpu_reference_time(sd, steps, max(1, min(args.warmup, 1)), clips=1)
@@ -638,7 +655,7 @@ def main():
         }
         if frame_shard is not None:
             out["frame_shard"] = frame_shard
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and n_gpus == 1:              # reported on rank 0 at N = 1 only (the reference arm covers every N)
             v, ms, cores = cpu_reference_time(sd, 3, 1, clips=1)
             out["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"1 clip (T={T}, {H}x{W}), 3 timed forwards after 1 warm-up, fp32 CPU oracle, "
